@@ -1,0 +1,530 @@
+// C ABI of libdigicamtoy_sm100.so (declared in include/digicamtoy_b200.h).
+// Host-side only: builds the device parameter block, picks launch geometry, launches kernels.
+#include "../../include/digicamtoy_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "device_params.cuh"
+#include "generate.cuh"
+#include "sweep.cuh"
+#include "replay.cuh"
+#include "stats.cuh"
+#include "selftest.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(DCT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+struct DeviceArena {
+    // one allocation for all parameter arrays
+    unsigned char* base = nullptr;
+    size_t size = 0;
+};
+
+}  // namespace
+
+struct dct_handle {
+    int device = 0;
+    int sm_count = 148;
+    dct::DevParams p{};
+    DeviceArena arena;
+    int kernel = DCT_KERNEL_SCATTER;
+    int gen_threads = dct::GEN_THREADS;
+    bool poly = false;
+    bool table_in_smem = false;
+    int n_table_entries = 0;
+    size_t gen_smem = 0;
+    double mean_pe_per_trace = 0.0;
+    // host-output pipeline (dct_generate_host), created lazily
+    cudaStream_t s_gen = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    int16_t* d_chunk[2] = {nullptr, nullptr};
+    float* d_sig[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int16_t* h_stage[2] = {nullptr, nullptr};
+    uint32_t chunk_events = 0;
+};
+
+namespace {
+
+template <typename T>
+size_t arena_reserve(size_t& cursor, size_t n) {
+    cursor = (cursor + 255) & ~(size_t)255;
+    size_t at = cursor;
+    cursor += n * sizeof(T);
+    return at;
+}
+
+// evaluates the (already normalised) spline in double, inclusive ends
+double spline_at(const dct_config* c, double x) {
+    const int n_iv = (int)c->n_knots - 1;
+    const double x_lo = c->knot_x[0], x_hi = c->knot_x[n_iv];
+    if (!(x >= x_lo && x <= x_hi)) return 0.0;
+    const double dx = (x_hi - x_lo) / n_iv;
+    int m = (int)std::floor((x - x_lo) / dx);
+    m = std::max(0, std::min(m, n_iv - 1));
+    if (m > 0 && x < c->knot_x[m]) --m;
+    else if (m < n_iv - 1 && x >= c->knot_x[m + 1]) ++m;
+    const double u = x - c->knot_x[m];
+    const double* k = c->coef + 4 * m;
+    return ((k[3] * u + k[2]) * u + k[1]) * u + k[0];
+}
+
+int validate(const dct_config* c) {
+    if (!c) return fail(DCT_E_ARG, "config is NULL");
+    if (c->struct_size != sizeof(dct_config))
+        return fail(DCT_E_ARG, "dct_config.struct_size %u != %zu (ABI mismatch)", c->struct_size,
+                    sizeof(dct_config));
+    if (c->n_pixels == 0 || c->n_pulses == 0 || c->n_bins == 0)
+        return fail(DCT_E_ARG, "n_pixels, n_pulses and n_bins must be > 0");
+    if (c->n_knots < 4) return fail(DCT_E_ARG, "template needs >= 4 knots");
+    if (!(c->dt > 0.0) || !(c->t_end > c->t0)) return fail(DCT_E_ARG, "bad time grid");
+    if (c->adc_min > c->adc_max || c->adc_min < -32768 || c->adc_max > 32767)
+        return fail(DCT_E_ARG, "saturation range must fit int16");
+    const void* ptrs[] = {c->nsb_rate, c->crosstalk, c->gain, c->sigma_1, c->sigma_e, c->baseline,
+                          c->n_photon, c->time_signal, c->jitter, c->knot_x, c->coef};
+    for (const void* q : ptrs)
+        if (!q) return fail(DCT_E_ARG, "a required config array is NULL");
+    const int n_iv = (int)c->n_knots - 1;
+    const double dx = (c->knot_x[n_iv] - c->knot_x[0]) / n_iv;
+    if (!(dx > 0.0)) return fail(DCT_E_ARG, "template knots must ascend");
+    for (int i = 0; i <= n_iv; ++i)
+        if (std::fabs(c->knot_x[i] - (c->knot_x[0] + i * dx)) > 1e-9 * std::max(1.0, std::fabs(dx)))
+            return fail(DCT_E_UNSUPPORTED, "template knots must be uniformly spaced");
+    for (uint32_t i = 0; i < c->n_pixels; ++i) {
+        if (!(c->crosstalk[i] >= 0.0 && c->crosstalk[i] < 1.0))
+            return fail(DCT_E_ARG, "crosstalk[%u]=%g outside [0,1)", i, c->crosstalk[i]);
+        if (!(c->nsb_rate[i] >= 0.0)) return fail(DCT_E_ARG, "nsb_rate[%u] negative", i);
+        if (!std::isfinite(c->gain[i]) || !std::isfinite(c->baseline[i]))
+            return fail(DCT_E_ARG, "gain/baseline[%u] not finite", i);
+    }
+    return DCT_OK;
+}
+
+void free_pipeline(dct_handle* h) {
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_chunk[i]) cudaFree(h->d_chunk[i]);
+        if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
+        for (int j = 0; j < 2; ++j)
+            if (h->d_sig[i][j]) cudaFree(h->d_sig[i][j]);
+        if (h->ev_gen[i]) cudaEventDestroy(h->ev_gen[i]);
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+        h->d_chunk[i] = nullptr; h->h_stage[i] = nullptr;
+        h->d_sig[i][0] = h->d_sig[i][1] = nullptr;
+        h->ev_gen[i] = h->ev_copy[i] = nullptr;
+    }
+    if (h->s_gen) cudaStreamDestroy(h->s_gen);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    h->s_gen = h->s_copy = nullptr;
+    h->chunk_events = 0;
+}
+
+template <bool POLY, int NT>
+int launch_scatter(dct_handle* h, const dct::GenArgs& a, cudaStream_t st) {
+    auto kern = dct::k_generate_scatter<POLY, NT>;
+    static thread_local size_t configured[16] = {0};
+    if (h->gen_smem > 48 * 1024 && configured[h->device & 15] < h->gen_smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gen_smem));
+        configured[h->device & 15] = h->gen_smem;
+    }
+    const uint64_t blocks = (a.n_traces + NT - 1) / NT;
+    if (blocks > 0x7fffffffull) return fail(DCT_E_ARG, "too many traces for one launch");
+    kern<<<(unsigned)blocks, NT, h->gen_smem, st>>>(a);
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dct_abi_version(void) { return DCT_ABI_VERSION; }
+const char* dct_last_error(void) { return g_err; }
+
+int dct_create(const dct_config* c, int device, dct_handle** out) {
+    if (!out) return fail(DCT_E_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = validate(c);
+    if (rc) return rc;
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    if (n_dev <= 0) return fail(DCT_E_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(DCT_E_ARG, "device %d out of range", device);
+    CK(cudaSetDevice(device));
+
+    dct_handle* h = new (std::nothrow) dct_handle();
+    if (!h) return fail(DCT_E_NOMEM, "out of host memory");
+    h->device = device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+
+    const int P = (int)c->n_pixels, K = (int)c->n_pulses, n_iv = (int)c->n_knots - 1;
+    dct::DevParams& p = h->p;
+    p.P = P; p.K = K; p.B = (int)c->n_bins; p.n_drop = (int)c->n_drop; p.n_iv = n_iv;
+    p.poisson = (int)c->poisson; p.sub_binning = (int)c->sub_binning;
+    p.adc_min = c->adc_min; p.adc_max = c->adc_max;
+    const double x_lo = c->knot_x[0], x_hi = c->knot_x[n_iv];
+    const double dx = (x_hi - x_lo) / n_iv;
+    p.dt = (float)c->dt; p.inv_dt = (float)(1.0 / c->dt);
+    p.span = (float)(c->t_end - c->t0);
+    p.x_lo = (float)x_lo; p.L = (float)(x_hi - x_lo);
+    p.knot_dx = (float)dx; p.inv_knot_dx = (float)(1.0 / dx);
+    p.t0f = (float)c->t0;
+    const double cell0 = std::floor(x_lo / c->dt + 1e-12);
+    p.cell0 = (int)cell0;
+    p.off0 = (float)std::max(0.0, x_lo - cell0 * c->dt);
+    p.t0_d = c->t0; p.dt_d = c->dt; p.x_lo_d = x_lo; p.x_hi_d = x_hi; p.inv_knot_dx_d = 1.0 / dx;
+
+    // polyphase decomposition: possible when the sampling period is a whole number of knot steps
+    const double ratio = c->dt / dx;
+    const double nph = std::floor(ratio + 0.5);
+    p.n_phase = 0; p.n_taps = 0;
+    if (nph >= 1.0 && nph <= 64.0 && std::fabs(ratio - nph) < 1e-9 * ratio) {
+        p.n_phase = (int)nph;
+        p.n_taps = (n_iv + p.n_phase - 1) / p.n_phase;
+    }
+    // on-grid taps
+    const int m_lo = (int)std::ceil(x_lo / c->dt - 1e-9), m_hi = (int)std::floor(x_hi / c->dt + 1e-9);
+    p.grid_m_lo = m_lo; p.grid_n = std::max(0, m_hi - m_lo + 1);
+
+    // ---- host staging of every device array
+    std::vector<float> f_rate(P), f_inv(P), f_xt(P), f_exp(P), f_gain(P), f_s1(P), f_se(P), f_base(P);
+    std::vector<double> d_gain(P), d_base(P);
+    std::vector<float> f_npe((size_t)P * K), f_tsig((size_t)P * K), f_jit((size_t)P * K);
+    double pe_sum = 0.0;
+    for (int i = 0; i < P; ++i) {
+        f_rate[i] = (float)c->nsb_rate[i];
+        f_inv[i] = c->nsb_rate[i] > 0.0 ? (float)(1.0 / c->nsb_rate[i]) : 0.0f;
+        f_xt[i] = (float)c->crosstalk[i];
+        f_exp[i] = (float)std::exp(-c->crosstalk[i]);
+        f_gain[i] = (float)c->gain[i];
+        f_s1[i] = (float)c->sigma_1[i];
+        f_se[i] = (float)c->sigma_e[i];
+        f_base[i] = (float)c->baseline[i];
+        d_gain[i] = c->gain[i];
+        d_base[i] = c->baseline[i];
+        pe_sum += c->nsb_rate[i] * (c->t_end - c->t0);
+    }
+    h->mean_pe_per_trace = pe_sum / P;
+    for (size_t i = 0; i < (size_t)P * K; ++i) {
+        f_npe[i] = (float)c->n_photon[i];
+        f_tsig[i] = (float)c->time_signal[i];
+        f_jit[i] = (float)c->jitter[i];
+    }
+    std::vector<float> f_coef((size_t)n_iv * 4);
+    for (size_t i = 0; i < (size_t)n_iv * 4; ++i) f_coef[i] = (float)c->coef[i];
+    std::vector<float> f_poly((size_t)p.n_taps * p.n_phase * 4, 0.0f);
+    for (int j = 0; j < p.n_taps; ++j)
+        for (int f = 0; f < p.n_phase; ++f) {
+            const int m = f + p.n_phase * j;
+            if (m < n_iv)
+                for (int q = 0; q < 4; ++q)
+                    f_poly[((size_t)j * p.n_phase + f) * 4 + q] = (float)c->coef[4 * m + q];
+        }
+    std::vector<float> f_grid((size_t)std::max(1, p.grid_n));
+    for (int m = 0; m < p.grid_n; ++m) f_grid[m] = (float)spline_at(c, (m_lo + m) * c->dt);
+
+    // ---- one arena
+    size_t cur = 0;
+    const size_t o_rate = arena_reserve<float>(cur, P), o_inv = arena_reserve<float>(cur, P),
+                 o_xt = arena_reserve<float>(cur, P), o_exp = arena_reserve<float>(cur, P),
+                 o_gain = arena_reserve<float>(cur, P), o_s1 = arena_reserve<float>(cur, P),
+                 o_se = arena_reserve<float>(cur, P), o_base = arena_reserve<float>(cur, P),
+                 o_dgain = arena_reserve<double>(cur, P), o_dbase = arena_reserve<double>(cur, P),
+                 o_npe = arena_reserve<float>(cur, (size_t)P * K),
+                 o_tsig = arena_reserve<float>(cur, (size_t)P * K),
+                 o_jit = arena_reserve<float>(cur, (size_t)P * K),
+                 o_c32 = arena_reserve<float>(cur, (size_t)n_iv * 4),
+                 o_c64 = arena_reserve<double>(cur, (size_t)n_iv * 4),
+                 o_kn = arena_reserve<double>(cur, (size_t)n_iv + 1),
+                 o_poly = arena_reserve<float>(cur, f_poly.size() + 4),
+                 o_grid = arena_reserve<float>(cur, f_grid.size());
+    h->arena.size = cur + 256;
+    cudaError_t e = cudaMalloc(&h->arena.base, h->arena.size);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(DCT_E_CUDA, "cudaMalloc(%zu) failed: %s", cur, cudaGetErrorString(e));
+    }
+    unsigned char* base = h->arena.base;
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpy(base + off, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t ue = cudaSuccess;
+#define UP(off, vec) if (ue == cudaSuccess) ue = up(off, (vec).data(), (vec).size() * sizeof((vec)[0]))
+    UP(o_rate, f_rate); UP(o_inv, f_inv); UP(o_xt, f_xt); UP(o_exp, f_exp); UP(o_gain, f_gain);
+    UP(o_s1, f_s1); UP(o_se, f_se); UP(o_base, f_base); UP(o_dgain, d_gain); UP(o_dbase, d_base);
+    UP(o_npe, f_npe); UP(o_tsig, f_tsig); UP(o_jit, f_jit); UP(o_c32, f_coef); UP(o_poly, f_poly);
+    UP(o_grid, f_grid);
+#undef UP
+    if (ue == cudaSuccess) ue = up(o_c64, c->coef, (size_t)n_iv * 4 * sizeof(double));
+    if (ue == cudaSuccess) ue = up(o_kn, c->knot_x, ((size_t)n_iv + 1) * sizeof(double));
+    if (ue != cudaSuccess) {
+        cudaFree(h->arena.base);
+        delete h;
+        return fail(DCT_E_CUDA, "parameter upload failed: %s", cudaGetErrorString(ue));
+    }
+    p.rate = (const float*)(base + o_rate); p.inv_rate = (const float*)(base + o_inv);
+    p.xt = (const float*)(base + o_xt); p.exp_neg_xt = (const float*)(base + o_exp);
+    p.gain = (const float*)(base + o_gain); p.sigma1 = (const float*)(base + o_s1);
+    p.sigma_e = (const float*)(base + o_se); p.baseline = (const float*)(base + o_base);
+    p.gain_d = (const double*)(base + o_dgain); p.baseline_d = (const double*)(base + o_dbase);
+    p.npe = (const float*)(base + o_npe); p.tsig = (const float*)(base + o_tsig);
+    p.jitter = (const float*)(base + o_jit);
+    p.coef32 = (const float4*)(base + o_c32); p.coef64 = (const double*)(base + o_c64);
+    p.knots = (const double*)(base + o_kn); p.poly = (const float4*)(base + o_poly);
+    p.grid_tap = (const float*)(base + o_grid);
+
+    // ---- kernel selection and launch geometry
+    h->poly = p.n_phase > 0 && p.sub_binning <= 0;
+    h->table_in_smem = !h->poly && n_iv <= 4096;
+    h->n_table_entries = h->poly ? p.n_taps * p.n_phase : (h->table_in_smem ? n_iv : 0);
+    h->gen_threads = dct::GEN_THREADS;
+    h->gen_smem = dct::gen_smem_bytes(p.B, h->n_table_entries, h->gen_threads);
+    const size_t smem_cap = 227 * 1024;
+    if (h->gen_smem > smem_cap) {
+        h->gen_threads = 32;
+        h->gen_smem = dct::gen_smem_bytes(p.B, h->n_table_entries, h->gen_threads);
+    }
+    if (h->gen_smem > smem_cap) {
+        cudaFree(h->arena.base);
+        delete h;
+        return fail(DCT_E_UNSUPPORTED, "trace of %d bins does not fit shared memory", p.B);
+    }
+    const bool sweep_ok = dct::sweep_supported(p);
+    int want = (int)c->kernel;
+    if (want == DCT_KERNEL_SWEEP && !sweep_ok) {
+        cudaFree(h->arena.base);
+        delete h;
+        return fail(DCT_E_UNSUPPORTED,
+                    "sweep kernel needs the polyphase table with %d taps, continuous NSB and <= %d bins",
+                    dct::SWEEP_TAPS, dct::SWEEP_MAX_BINS);
+    }
+    if (want == DCT_KERNEL_AUTO)
+        want = (sweep_ok && h->mean_pe_per_trace >= dct::SWEEP_MIN_MEAN_PE) ? DCT_KERNEL_SWEEP
+                                                                            : DCT_KERNEL_SCATTER;
+    h->kernel = want;
+    g_err[0] = 0;
+    *out = h;
+    return DCT_OK;
+}
+
+void dct_destroy(dct_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_pipeline(h);
+    if (h->arena.base) cudaFree(h->arena.base);
+    delete h;
+}
+
+int dct_selected_kernel(const dct_handle* h) { return h ? h->kernel : DCT_E_ARG; }
+
+int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
+                 float* sig_time, float* sig_charge, void* stream) {
+    if (!h || !adc) return fail(DCT_E_ARG, "handle or adc is NULL");
+    if (n_events == 0) return DCT_OK;
+    if ((first_event + n_events) >> 56) return fail(DCT_E_ARG, "event index exceeds 2^56");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    dct::GenArgs a;
+    a.p = h->p;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.first_event = first_event;
+    a.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
+    a.adc = adc; a.sig_time = sig_time; a.sig_charge = sig_charge;
+    a.table_in_smem = h->table_in_smem ? 1 : 0;
+    if (h->kernel == DCT_KERNEL_SWEEP) return dct::launch_sweep(h->device, h->sm_count, a, st, g_err, sizeof(g_err));
+    if (h->gen_threads == 32)
+        return h->poly ? launch_scatter<true, 32>(h, a, st) : launch_scatter<false, 32>(h, a, st);
+    return h->poly ? launch_scatter<true, dct::GEN_THREADS>(h, a, st)
+                   : launch_scatter<false, dct::GEN_THREADS>(h, a, st);
+}
+
+int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
+                      int16_t* adc_host, float* sig_time_host, float* sig_charge_host) {
+    if (!h || !adc_host) return fail(DCT_E_ARG, "handle or adc_host is NULL");
+    if (n_events == 0) return DCT_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t trace_bytes = (size_t)h->p.P * h->p.B * sizeof(int16_t);
+    const size_t sig_elems = (size_t)h->p.P * h->p.K;
+    if (!h->s_gen) {
+        // chunk ~64 MiB: large enough to amortise launches, small enough to pipeline
+        uint32_t ce = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / trace_bytes);
+        h->chunk_events = ce;
+        CK(cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+            CK(cudaMalloc(&h->d_chunk[i], ce * trace_bytes));
+            CK(cudaMalloc(&h->d_sig[i][0], ce * sig_elems * sizeof(float)));
+            CK(cudaMalloc(&h->d_sig[i][1], ce * sig_elems * sizeof(float)));
+        }
+    }
+    // Is the destination page-locked?  Then copy straight into it; otherwise go through pinned staging.
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, adc_host) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && !h->h_stage[0])
+        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&h->h_stage[i], h->chunk_events * trace_bytes));
+
+    const uint32_t ce = h->chunk_events;
+    const uint32_t n_chunks = (n_events + ce - 1) / ce;
+    struct Pending { int16_t* dst; size_t bytes; bool live; } pend[2] = {{nullptr, 0, false}, {nullptr, 0, false}};
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const int slot = (int)(c & 1);
+        const uint32_t e0 = c * ce, ne = std::min(ce, n_events - e0);
+        // the slot's previous copy must have drained before we overwrite its device buffer
+        if (c >= 2) {
+            CK(cudaEventSynchronize(h->ev_copy[slot]));
+            if (pend[slot].live) { memcpy(pend[slot].dst, h->h_stage[slot], pend[slot].bytes); pend[slot].live = false; }
+        }
+        int rc = dct_generate(h, seed, first_event + e0, ne, h->d_chunk[slot],
+                              sig_time_host ? h->d_sig[slot][0] : nullptr,
+                              sig_charge_host ? h->d_sig[slot][1] : nullptr, h->s_gen);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_gen[slot], h->s_gen));
+        CK(cudaStreamWaitEvent(h->s_copy, h->ev_gen[slot], 0));
+        int16_t* dst = adc_host + (size_t)e0 * h->p.P * h->p.B;
+        if (pinned) {
+            CK(cudaMemcpyAsync(dst, h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+        } else {
+            CK(cudaMemcpyAsync(h->h_stage[slot], h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+            pend[slot].dst = dst; pend[slot].bytes = ne * trace_bytes; pend[slot].live = true;
+        }
+        if (sig_time_host)
+            CK(cudaMemcpyAsync(sig_time_host + (size_t)e0 * sig_elems, h->d_sig[slot][0],
+                               ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy));
+        if (sig_charge_host)
+            CK(cudaMemcpyAsync(sig_charge_host + (size_t)e0 * sig_elems, h->d_sig[slot][1],
+                               ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy));
+        CK(cudaEventRecord(h->ev_copy[slot], h->s_copy));
+        // generation of the next chunk in this slot's sibling may start right away
+    }
+    CK(cudaStreamSynchronize(h->s_copy));
+    for (int s = 0; s < 2; ++s)
+        if (pend[s].live) memcpy(pend[s].dst, h->h_stage[s], pend[s].bytes);
+    CK(cudaStreamSynchronize(h->s_gen));
+    return DCT_OK;
+}
+
+static int replay_common(bool f64, dct_handle* h, uint32_t n_events, const int64_t* nsb_offsets,
+                         const double* nsb_time, const double* nsb_amp, const double* sig_time,
+                         const double* sig_amp, const double* e_noise, int16_t* adc,
+                         unsigned long long* n_clamped, void* stream) {
+    if (!h || !nsb_offsets || !sig_time || !sig_amp || !adc)
+        return fail(DCT_E_ARG, "a required replay pointer is NULL");
+    if (h->p.sub_binning > 0) { /* lists are explicit; nothing mode-specific */ }
+    if (n_events == 0) return DCT_OK;
+    CK(cudaSetDevice(h->device));
+    dct::ReplayArgs a;
+    a.p = h->p;
+    a.n_traces = (uint64_t)n_events * h->p.P;
+    a.nsb_offsets = nsb_offsets; a.nsb_time = nsb_time; a.nsb_amp = nsb_amp;
+    a.sig_time = sig_time; a.sig_amp = sig_amp; a.e_noise = e_noise; a.adc = adc;
+    a.n_clamped = n_clamped;
+    const uint64_t blocks = (a.n_traces + dct::REPLAY_WARPS - 1) / dct::REPLAY_WARPS;
+    if (blocks > 0x7fffffffull) return fail(DCT_E_ARG, "too many traces for one launch");
+    const size_t smem = (size_t)h->p.n_iv * 4 * (f64 ? sizeof(double) : sizeof(float));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64) {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(dct::k_replay<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dct::k_replay<double><<<(unsigned)blocks, dct::REPLAY_WARPS * 32, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(dct::k_replay<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dct::k_replay<float><<<(unsigned)blocks, dct::REPLAY_WARPS * 32, smem, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+int dct_replay_f64(dct_handle* h, uint32_t n_events, const int64_t* nsb_offsets, const double* nsb_time,
+                   const double* nsb_amp, const double* sig_time, const double* sig_amp,
+                   const double* e_noise, int16_t* adc, unsigned long long* n_clamped, void* stream) {
+    return replay_common(true, h, n_events, nsb_offsets, nsb_time, nsb_amp, sig_time, sig_amp, e_noise,
+                         adc, n_clamped, stream);
+}
+
+int dct_replay_f32(dct_handle* h, uint32_t n_events, const int64_t* nsb_offsets, const double* nsb_time,
+                   const double* nsb_amp, const double* sig_time, const double* sig_amp,
+                   const double* e_noise, int16_t* adc, unsigned long long* n_clamped, void* stream) {
+    return replay_common(false, h, n_events, nsb_offsets, nsb_time, nsb_amp, sig_time, sig_amp, e_noise,
+                         adc, n_clamped, stream);
+}
+
+int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
+                         unsigned long long* adc_hist, double* bin_sum, double* bin_sumsq,
+                         double* pixel_sum, double* pixel_sumsq, unsigned long long* charge_hist,
+                         int32_t charge_lo, uint32_t n_charge_bins, double* moments, void* stream) {
+    if (!h || !adc) return fail(DCT_E_ARG, "handle or adc is NULL");
+    if (n_events == 0) return DCT_OK;
+    CK(cudaSetDevice(h->device));
+    dct::StatsArgs a;
+    a.P = h->p.P; a.B = h->p.B; a.adc_min = h->p.adc_min; a.adc_max = h->p.adc_max;
+    a.n_traces = (uint64_t)n_events * h->p.P;
+    a.adc = adc; a.baseline = h->p.baseline;
+    a.adc_hist = adc_hist; a.bin_sum = bin_sum; a.bin_sumsq = bin_sumsq;
+    a.pixel_sum = pixel_sum; a.pixel_sumsq = pixel_sumsq; a.charge_hist = charge_hist;
+    a.charge_lo = charge_lo; a.n_charge_bins = (int)n_charge_bins; a.moments = moments;
+    const int n_hist = a.adc_max - a.adc_min + 1;
+    if (adc_hist && n_hist > 16384) return fail(DCT_E_UNSUPPORTED, "ADC histogram wider than 16384 bins");
+    if (charge_hist && (a.B > 32 * dct::STATS_BINS_PER_LANE || n_charge_bins == 0))
+        return fail(DCT_E_UNSUPPORTED, "charge histogram needs <= 128 bins per trace and n_charge_bins > 0");
+    const size_t smem = adc_hist ? (size_t)n_hist * sizeof(unsigned int) : 0;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(dct::k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t warps_needed = a.n_traces;
+    uint64_t blocks = (warps_needed + (dct::STATS_THREADS / 32) - 1) / (dct::STATS_THREADS / 32);
+    blocks = std::min<uint64_t>(blocks, (uint64_t)h->sm_count * 8);
+    dct::k_stats<<<(unsigned)blocks, dct::STATS_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+int dct_write_calibrate(int16_t* buf, size_t n, void* stream) {
+    if (!buf) return fail(DCT_E_ARG, "buf is NULL");
+    if (reinterpret_cast<uintptr_t>(buf) & 15) return fail(DCT_E_ARG, "buf must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t n_vec = n / 8, n_tail = n - n_vec * 8;
+    dct::k_write_calibrate<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<int4*>(buf), n_vec, buf + n_vec * 8, n_tail);
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+int dct_test_sample(uint32_t kind, double a, double b, uint64_t seed, uint32_t n, float* out, void* stream) {
+    if (!out) return fail(DCT_E_ARG, "out is NULL");
+    if (n == 0) return DCT_OK;
+    dct::k_test_sample<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        kind, (float)a, (float)b, (uint32_t)seed, (uint32_t)(seed >> 32), n, out);
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// Test hook: draws n samples from one of the device samplers so the host tests can compare each
+// distribution with its closed form.  Not used by the product path.
+#pragma once
+#include "sampling.cuh"
+
+namespace dct {
+
+enum : uint32_t { SAMPLE_NORMAL = 0, SAMPLE_EXP_GAP = 1, SAMPLE_BOREL = 2, SAMPLE_POISSON = 3,
+                  SAMPLE_BRANCHING = 4, SAMPLE_UNIFORM = 5 };
+
+__global__ void k_test_sample(uint32_t kind, float a, float b, uint32_t k0, uint32_t k1, uint32_t n,
+                              float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StreamKey key;
+    key.k0 = k0; key.k1 = k1; key.ev_lo = i; key.ev_hi = 0; key.pixel = 7;
+    const u32x4 r = draw_block(key, STREAM_NSB, 0);
+    float v = 0.0f;
+    switch (kind) {
+        case SAMPLE_NORMAL: v = normal_one(r.z, r.w); break;
+        case SAMPLE_EXP_GAP: v = exp_gap(r.x, a); break;
+        case SAMPLE_BOREL: v = (float)borel(r.y, a, __expf(-a)); break;
+        case SAMPLE_POISSON: { BlockReader rd(key, STREAM_BRANCH, 0); v = (float)poisson(rd, a); } break;
+        case SAMPLE_BRANCHING: { BlockReader rd(key, STREAM_BRANCH, 0); v = (float)branching_total(rd, (int)b, a); } break;
+        case SAMPLE_UNIFORM: v = u01_open1(r.x); break;
+        default: break;
+    }
+    out[i] = v;
+}
+
+}  // namespace dct

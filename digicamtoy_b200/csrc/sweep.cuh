@@ -1,0 +1,127 @@
+// K1, high-rate variant: time-ordered sweep with a register window.
+//
+// The NSB photo-electrons of a trace come out of the exponential-gap generator already sorted
+// in time.  A pe whose onset lies in sampling cell c only touches bins c+1 .. c+TAPS, so a thread
+// keeps exactly those TAPS partial sums in registers (statically indexed), adds each pe with one
+// 16-byte shared-memory load + 4 FFMA per tap (polyphase table, immediate offsets), and when the
+// onset moves to the next cell it retires the oldest bin to shared memory and slides the window.
+// No per-tap address arithmetic, no read-modify-write of shared memory.
+//
+// It consumes the same Philox blocks and performs the same floating-point operations per bin, in
+// the same order, as k_generate_scatter: both kernels produce identical cubes (tests check it).
+//
+// Replaces the dense (pixel, pe, bin) spline evaluation of compute_analog_signal
+// (reference digicamtoy/tracegenerator/__init__.py:350-362).
+#pragma once
+#include "generate.cuh"
+
+namespace dct {
+
+constexpr int SWEEP_TAPS = 22;            // 88 ns template / 4 ns sampling
+constexpr int SWEEP_PHASES = 8;           // 4 ns sampling / 0.5 ns knots
+constexpr int SWEEP_THREADS = 128;
+constexpr int SWEEP_MAX_BINS = 256;
+constexpr double SWEEP_MIN_MEAN_PE = 24.0;   // below this the scatter kernel wins (few pe per trace)
+
+inline bool sweep_supported(const DevParams& p) {
+    return p.n_phase == SWEEP_PHASES && p.n_taps == SWEEP_TAPS && p.sub_binning <= 0 &&
+           p.B <= SWEEP_MAX_BINS &&
+           gen_smem_bytes(p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS) <= 227 * 1024;
+}
+
+template <int TAPS, int PHASES, int NT>
+__global__ void __launch_bounds__(NT)
+k_generate_sweep(const GenArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevParams& p = a.p;
+    const int tid = threadIdx.x;
+    const int B = p.B;
+
+    float* Vall = reinterpret_cast<float*>(smem_raw);
+    float4* tab_s = reinterpret_cast<float4*>(smem_raw + (size_t)B * NT * sizeof(float));
+    int16_t* out_s = reinterpret_cast<int16_t*>(tab_s + TAPS * PHASES);
+    for (int i = tid; i < TAPS * PHASES; i += NT) tab_s[i] = p.poly[i];
+    float* V = Vall + tid;
+    for (int b = 0; b < B; ++b) V[b * NT] = 0.0f;
+    __syncthreads();
+
+    const uint64_t trace0 = (uint64_t)blockIdx.x * NT;
+    if (trace0 + tid < a.n_traces) {
+        const TraceId t = trace_id(a, trace0 + tid);
+        const float rate = p.rate[t.pixel];
+        const float xt = p.xt[t.pixel];
+        const float exp_neg_xt = p.exp_neg_xt[t.pixel];
+        const float sigma1 = p.sigma1[t.pixel];
+
+        if (rate > 0.0f) {
+            const float inv_rate = p.inv_rate[t.pixel];
+            float W[TAPS];                                   // W[j] <-> simulated bin cell+1+j
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) W[j] = 0.0f;
+            float elapsed = 0.0f;
+            int cell = p.cell0;
+            float off = p.off0;
+            const int kb_shift = 1 - p.n_drop;               // kept index of W[0] = cell + kb_shift
+            for (uint32_t i = 0;; ++i) {
+                const u32x4 r = draw_block(t.key, STREAM_NSB, i);
+                const float gap = exp_gap(r.x, inv_rate);
+                elapsed += gap;
+                if (elapsed >= p.span) break;
+                const int cell_before = cell;
+                int k = advance_onset(p, gap, cell, off);
+                if (k >= TAPS) {
+                    // long gap: the whole window retires at once
+#pragma unroll
+                    for (int j = 0; j < TAPS; ++j) {
+                        const int kb = cell_before + kb_shift + j;
+                        if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[j];
+                        W[j] = 0.0f;
+                    }
+                } else {
+                    int kb = cell_before + kb_shift;
+                    for (; k > 0; --k, ++kb) {
+                        if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[0];
+#pragma unroll
+                        for (int j = 0; j < TAPS - 1; ++j) W[j] = W[j + 1];
+                        W[TAPS - 1] = 0.0f;
+                    }
+                }
+                const float A = nsb_amplitude(r, xt, exp_neg_xt, sigma1);
+                int f; float u;
+                phase_of(p, p.dt - off, f, u);
+                const float4* row = tab_s + f;
+#pragma unroll
+                for (int j = 0; j < TAPS; ++j) W[j] = __fmaf_rn(A, horner(row[j * PHASES], u), W[j]);
+            }
+            // retire what is left in the window
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+                const int kb = cell + kb_shift + j;
+                if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[j];
+            }
+        }
+        add_signal_pulses<NT>(a, t, p.coef32, V, xt, sigma1);
+        digitise_trace<NT>(p, t, V, out_s + tid * B);
+    }
+    __syncthreads();
+    store_run<NT>(a, trace0, out_s);
+}
+
+inline int launch_sweep(int device, int /*sm_count*/, const GenArgs& a, cudaStream_t st, char* err, size_t err_len) {
+    auto kern = k_generate_sweep<SWEEP_TAPS, SWEEP_PHASES, SWEEP_THREADS>;
+    const size_t smem = gen_smem_bytes(a.p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS);
+    static thread_local size_t configured[16] = {0};
+    if (smem > 48 * 1024 && configured[device & 15] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { snprintf(err, err_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+        configured[device & 15] = smem;
+    }
+    const uint64_t blocks = (a.n_traces + SWEEP_THREADS - 1) / SWEEP_THREADS;
+    if (blocks > 0x7fffffffull) { snprintf(err, err_len, "too many traces for one launch"); return -1; }
+    kern<<<(unsigned)blocks, SWEEP_THREADS, smem, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, err_len, "sweep launch failed: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+}  // namespace dct

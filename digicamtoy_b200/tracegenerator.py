@@ -1,0 +1,228 @@
+"""``NTraceGenerator``: the reference's generator API over the B200 kernels.
+
+Mirrors the constructor / iterator / attribute surface of the reference class
+(``digicamtoy/tracegenerator/__init__.py:38-226``) so that ``produce_data.py`` and the example
+scripts run unchanged, while the per-event Monte Carlo (:228-381) runs in
+``libdigicamtoy_sm100.so``.  Events are produced in device batches; the iterator hands them out
+one at a time from pinned host memory.
+
+Deliberate differences from the reference:
+  * ``n_events=n`` yields exactly n events (the reference yields n+1, against its own test).
+  * ADC counts saturate to ``saturate=(0, 4095)``; the reference wraps negatives and never clips.
+  * ``voltage_drop`` scales ``n_photon`` per pixel (the reference broadcasts (P,1)x(P,) to (P,P)).
+  * ``poisson=False`` uses ``round(n_photon)`` primaries (the reference raises on floats and
+    lets the configured value grow from event to event).
+  * the pe lists ``nsb_time / nsb_photon / mask`` never exist on the GPU path and are not exposed.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import native
+from .params import ARTIFICIAL_BACKWARD_TIME, build_params, evaluate_template, resolve_pulse_shape_file
+
+_KERNELS = {'auto': native.KERNEL_AUTO, 'scatter': native.KERNEL_SCATTER, 'sweep': native.KERNEL_SWEEP}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _resolve_device(device):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError('digicamtoy_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise ValueError('device must be a CUDA device, got {!r}'.format(device))
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+class NTraceGenerator:
+
+    def __init__(self, time_start=0, time_end=200, time_sampling=4, n_pixels=1296, nsb_rate=0.6,
+                 crosstalk=0.08, gain_nsb=True, n_photon=0, poisson=True, sigma_e=0.8, sigma_1=0.8,
+                 gain=5.8, baseline=200, time_signal=20, jitter=0,
+                 pulse_shape_file='/utils/pulse_SST-1M_pixel_0.dat', sub_binning=0, n_events=None,
+                 voltage_drop=False,
+                 # --- additions of this implementation (all optional)
+                 seed=None, device=None, batch_events=None, saturate=(0, 4095), verbose=False,
+                 kernel='auto', first_event=0,
+                 **kwargs):  # unknown keys are ignored: produce_data passes its whole option set (:113)
+        p = build_params(time_start=time_start, time_end=time_end, time_sampling=time_sampling,
+                         n_pixels=n_pixels, nsb_rate=nsb_rate, crosstalk=crosstalk, gain_nsb=gain_nsb,
+                         n_photon=n_photon, poisson=poisson, sigma_e=sigma_e, sigma_1=sigma_1,
+                         gain=gain, baseline=baseline, time_signal=time_signal, jitter=jitter,
+                         pulse_shape_file=pulse_shape_file, sub_binning=sub_binning,
+                         voltage_drop=voltage_drop)
+        self.params = p
+        # reference attribute names (row a11 of the survey)
+        self.artificial_backward_time = ARTIFICIAL_BACKWARD_TIME
+        self.n_samples = p.n_samples
+        self.time_start, self.time_end, self.time_sampling = p.time_start, p.time_end, p.time_sampling
+        self.n_pixels = p.n_pixels
+        self.n_photon, self.time_signal, self.jitter = p.n_photon, p.time_signal, p.jitter
+        self.poisson = p.poisson
+        self.filename_pulse_shape = resolve_pulse_shape_file(pulse_shape_file)
+        self.gain, self.sigma_e, self.sigma_1, self.baseline = p.gain, p.sigma_e, p.sigma_1, p.baseline
+        self.gain_nsb, self.voltage_drop = gain_nsb, voltage_drop
+        self.nsb_rate, self.crosstalk = p.nsb_rate, p.crosstalk
+        self.tau, self.true_baseline = p.tau, p.true_baseline
+        self.sub_binning = sub_binning
+        self.n_events = n_events
+        self.count = -1
+        if verbose:   # the three constructor print-outs of the reference (:130-135, :159-164)
+            print('Set NSB rate : {} [GHz] \tTrue NSB rate : {} [GHz]'.format(
+                p.set_nsb_rate.mean(), p.nsb_rate.mean()))
+            print('Set XT : {} [p.e.] \tTrue XT : {} [p.e.]'.format(
+                p.set_crosstalk.mean(), p.crosstalk.mean()))
+            print('Set Gain : {} [LSB/p.e.] \tTrue Gain : {} [LSB/p.e.]'.format(
+                p.set_gain.mean(), p.gain.mean()))
+            print('Set Baseline : {} [LSB]\tTrue Baseline : {} [LSB]\tTrue Baseline Shift : {} [LSB]'
+                  .format(p.baseline.mean(), p.true_baseline.mean(),
+                          p.true_baseline.mean() - p.baseline.mean()))
+
+        if saturate is None:
+            saturate = (-32768, 32767)
+        self.saturate = (int(saturate[0]), int(saturate[1]))
+        if kernel not in _KERNELS:
+            raise ValueError('kernel must be one of {}'.format(sorted(_KERNELS)))
+        self.seed = int.from_bytes(os.urandom(8), 'little') if seed is None else int(seed) & (2 ** 64 - 1)
+        self.first_event = int(first_event)
+        self.device = _resolve_device(device)
+        self._handle = native.Handle(p, device=self.device, adc_min=self.saturate[0],
+                                     adc_max=self.saturate[1], kernel=_KERNELS[kernel])
+        self.kernel = self._handle.kernel
+        if batch_events is None:
+            # ~32 MiB of ADC per batch keeps the per-event iterator responsive
+            batch_events = max(1, min(4096, (32 << 20) // (p.n_pixels * p.n_bins * 2)))
+        self.batch_events = int(batch_events)
+        self._host = None          # pinned (adc, time, charge) of the current batch
+        self._batch_first = 0      # event index (relative) of slot 0 of the current batch
+        self._batch_len = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ reference surface
+    def __str__(self):
+        return ''.join('{}{}'.format(k, v) for k, v in sorted(self.__dict__.items())
+                       if not k.startswith('_'))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self.next()
+        return self
+
+    @property
+    def pulse_template(self):
+        p = self.params
+        return lambda t: evaluate_template(p.knot_x, p.coef, t)
+
+    def get_pulse_shape(self, time, t_0=0, baseline=0, amplitude=1):
+        return amplitude * self.pulse_template(np.asarray(time) - t_0) + baseline        # :186-188
+
+    def reset(self):
+        """State before the first event (:190-199): zeros, all simulated bins."""
+        p = self.params
+        self.cherenkov_time = np.zeros(p.n_photon.shape)
+        self.cherenkov_photon = np.zeros(p.n_photon.shape, dtype=int)
+        self.sampling_bins = np.arange(p.time_start, p.time_end, p.time_sampling)
+        self.adc_count = np.zeros((p.n_pixels, self.sampling_bins.shape[0]))
+
+    def next(self):
+        if self.n_events is not None and self.count + 1 >= self.n_events:
+            raise StopIteration
+        self.count += 1
+        slot = self.count - self._batch_first
+        if self._host is None or slot >= self._batch_len or slot < 0:
+            self._fill_batch(self.count)
+            slot = 0
+        adc, t, q = self._host
+        self.adc_count = adc[slot]
+        self.cherenkov_time = t[slot]
+        self.cherenkov_photon = q[slot]
+        self.sampling_bins = self.params.sampling_bins
+
+    def __getattr__(self, name):
+        if name in ('nsb_time', 'nsb_photon', 'mask'):
+            raise AttributeError(
+                '{} is not materialised: photo-electrons live in GPU registers only '
+                '(use the oracle in oracle/reference_port.py to inspect pe lists)'.format(name))
+        raise AttributeError(name)
+
+    # ------------------------------------------------------------------ bulk API (device / host)
+    def generate(self, n_events, first_event=None, out=None, truth=False, stream=None):
+        """ADC cube of ``n_events`` events as a CUDA int16 tensor ``[n, P, B]`` (asynchronous).
+
+        ``first_event`` is the global event index (default: continue after the last bulk call);
+        the same (seed, event, pixel) always gives the same trace, whatever the batching or the
+        number of GPUs.  With ``truth=True`` also returns (time, charge) float32 ``[n, P, K]``."""
+        torch = _torch()
+        p = self.params
+        n_events = int(n_events)
+        if first_event is None:
+            first_event = self.first_event + getattr(self, '_bulk_cursor', 0)
+            self._bulk_cursor = getattr(self, '_bulk_cursor', 0) + n_events
+        dev = torch.device('cuda', self.device)
+        if out is None:
+            out = torch.empty((n_events, p.n_pixels, p.n_bins), dtype=torch.int16, device=dev)
+        elif (out.dtype != torch.int16 or not out.is_contiguous() or out.device != dev
+              or out.numel() != n_events * p.n_pixels * p.n_bins):
+            raise ValueError('out must be a contiguous int16 CUDA tensor of n*P*B elements')
+        t = q = None
+        if truth:
+            t = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32, device=dev)
+            q = torch.empty_like(t)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        if n_events:
+            self._handle.generate(self.seed, int(first_event), n_events, out.data_ptr(),
+                                  t.data_ptr() if truth else None, q.data_ptr() if truth else None,
+                                  stream)
+        return (out, t, q) if truth else out
+
+    def generate_host(self, n_events, first_event=None, out=None, truth=True):
+        """Same, into pinned host memory through the library's chunked D2H pipeline; returns
+        NumPy views ``(adc uint16/int16 [n,P,B], time f32 [n,P,K], charge f32 [n,P,K])``."""
+        torch = _torch()
+        p = self.params
+        n_events = int(n_events)
+        if first_event is None:
+            first_event = self.first_event
+        if out is None:
+            adc = torch.empty((n_events, p.n_pixels, p.n_bins), dtype=torch.int16).pin_memory()
+        else:
+            adc = out
+        t = q = None
+        if truth:
+            t = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory()
+            q = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory()
+        if n_events:
+            self._handle.generate_host(self.seed, int(first_event), n_events, adc.data_ptr(),
+                                       t.data_ptr() if truth else None,
+                                       q.data_ptr() if truth else None)
+        self._pinned_keepalive = (adc, t, q)
+        a = adc.numpy()
+        if self.saturate[0] >= 0:
+            a = a.view(np.uint16)
+        return (a, t.numpy(), q.numpy()) if truth else a
+
+    # ------------------------------------------------------------------ internals
+    def _fill_batch(self, first_relative):
+        n = self.batch_events
+        if self.n_events is not None:
+            n = min(n, self.n_events - first_relative)
+        self._host = self.generate_host(n, first_event=self.first_event + first_relative)
+        self._batch_first = first_relative
+        self._batch_len = n
+
+    def close(self):
+        self._handle.close()

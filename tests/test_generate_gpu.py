@@ -1,0 +1,353 @@
+"""T2-T4: the stochastic kernels through the C ABI -- determinism / geometry independence,
+scatter == sweep, per-sampler distributions, per-bin moments against the closed form, two-sample
+tests against the CPU oracle, saturation, iterator semantics, on-device statistics."""
+import numpy as np
+import pytest
+from scipy import stats as sps
+
+from oracle import reference_port as orc
+
+pytestmark = pytest.mark.gpu
+
+ACDC = dict(time_start=0, time_end=200, time_sampling=4, crosstalk=0.08, gain_nsb=True, poisson=True,
+            sigma_e=1.25, sigma_1=0.8, gain=5, baseline=280, time_signal=20, jitter=0.2)
+DARK = dict(time_start=0, time_end=368, time_sampling=4, nsb_rate=0.003, crosstalk=0.08,
+            gain_nsb=True, poisson=True, sigma_e=0.8, sigma_1=0.8, gain=5.8, baseline=200,
+            time_signal=0., jitter=0.3)
+
+
+def gen(**kw):
+    from digicamtoy_b200 import NTraceGenerator
+    return NTraceGenerator(**kw)
+
+
+def cube(g, n, first_event=0, truth=False):
+    import torch
+    out = g.generate(n, first_event=first_event, truth=truth)
+    torch.cuda.synchronize()
+    if truth:
+        return tuple(t.cpu().numpy() for t in out)
+    return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------ determinism / geometry
+@pytest.mark.parametrize('kernel', ['scatter', 'sweep'])
+def test_chunking_and_offsets_do_not_change_bits(kernel):
+    g = gen(n_pixels=37, nsb_rate=0.5, n_photon=8., seed=99, kernel=kernel, **ACDC)
+    whole = cube(g, 40)
+    parts = np.concatenate([cube(g, 7, 0), cube(g, 13, 7), cube(g, 20, 20)])
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(cube(g, 5, first_event=17), whole[17:22])       # any range is regenerable
+    g2 = gen(n_pixels=37, nsb_rate=0.5, n_photon=8., seed=99, kernel=kernel, **ACDC)
+    assert np.array_equal(cube(g2, 40), whole)                             # same seed, new handle
+    g3 = gen(n_pixels=37, nsb_rate=0.5, n_photon=8., seed=100, kernel=kernel, **ACDC)
+    assert not np.array_equal(cube(g3, 40), whole)
+
+
+@pytest.mark.parametrize('rate,npe', [(1.0, 100.), (0.125, 10.), (0.04, 0.), (0.003, 1.)])
+def test_sweep_and_scatter_kernels_are_bit_identical(rate, npe):
+    a = gen(n_pixels=200, nsb_rate=rate, n_photon=npe, seed=5, kernel='scatter', **ACDC)
+    b = gen(n_pixels=200, nsb_rate=rate, n_photon=npe, seed=5, kernel='sweep', **ACDC)
+    assert a.kernel == 'scatter' and b.kernel == 'sweep'
+    ca, ta, qa = cube(a, 24, truth=True)
+    cb, tb, qb = cube(b, 24, truth=True)
+    assert np.array_equal(ca, cb)
+    assert np.array_equal(ta, tb) and np.array_equal(qa, qb)
+
+
+def test_sweep_scatter_identical_with_per_pixel_rates_and_dark_window():
+    kw = dict(DARK)
+    kw['nsb_rate'] = np.concatenate([np.zeros(3), np.logspace(-3, 0.3, 61)])
+    a = gen(n_pixels=64, n_photon=2, seed=1, kernel='scatter', **kw)
+    b = gen(n_pixels=64, n_photon=2, seed=1, kernel='sweep', **kw)
+    assert np.array_equal(cube(a, 30), cube(b, 30))
+
+
+def test_host_path_equals_device_path():
+    g = gen(n_pixels=1296, nsb_rate=0.125, n_photon=10., seed=3, **ACDC)
+    dev, t, q = cube(g, 700, truth=True)           # > one 64 MiB chunk of the host pipeline
+    adc, th, qh = g.generate_host(700, first_event=0)
+    assert adc.dtype == np.uint16
+    assert np.array_equal(adc.view(np.int16), dev)
+    assert np.array_equal(th, t) and np.array_equal(qh, q)
+    # pageable destination
+    import ctypes
+    buf = np.empty((700, 1296, 50), dtype=np.int16)
+    g._handle.generate_host(g.seed, 0, 700, buf.ctypes.data)
+    assert np.array_equal(buf, dev)
+
+
+# ------------------------------------------------------------------ the samplers, one by one
+def _sample(kind, a=0.0, b=0.0, n=400000, seed=11):
+    import torch
+    from digicamtoy_b200 import native
+    out = torch.empty(n, dtype=torch.float32, device='cuda')
+    native.test_sample(kind, a, b, seed, n, out.data_ptr())
+    torch.cuda.synchronize()
+    return out.cpu().numpy().astype(np.float64)
+
+
+def test_uniform_and_normal_samplers():
+    u = _sample('uniform')
+    assert u.min() >= 0 and u.max() < 1
+    assert sps.kstest(u, 'uniform').pvalue > 1e-3
+    z = _sample('normal')
+    assert sps.kstest(z, 'norm').pvalue > 1e-3
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 0.01
+    assert abs(sps.kurtosis(z)) < 0.05
+
+
+def test_exponential_gap_sampler():
+    x = _sample('exp_gap', a=2.5)
+    assert sps.kstest(x, 'expon', args=(0, 2.5)).pvalue > 1e-3
+
+
+@pytest.mark.parametrize('xt', [0.0, 0.08, 0.3, 0.6])
+def test_borel_sampler_matches_closed_form(xt):
+    n = _sample('borel', a=xt)
+    if xt == 0:
+        assert np.all(n == 1)
+        return
+    pmf = orc.borel_pmf(xt, 200)
+    kmax = int(np.searchsorted(-pmf * n.size, -8)) + 1       # bins with >= 8 expected
+    obs = np.bincount(n.astype(int), minlength=kmax + 2)[1:kmax + 1].astype(float)
+    exp = pmf[:kmax] * n.size
+    obs = np.append(obs, n.size - obs.sum())
+    exp = np.append(exp, n.size - exp.sum())
+    chi2 = ((obs - exp) ** 2 / exp).sum()
+    assert sps.chi2.sf(chi2, len(obs) - 1) > 1e-3, (chi2, len(obs))
+    assert abs(n.mean() - 1 / (1 - xt)) < 5 * np.sqrt(xt / (1 - xt) ** 3 / n.size)
+
+
+@pytest.mark.parametrize('lam', [0.012, 0.7, 4.0, 11.9, 12.1, 100.0, 3162.0])
+def test_poisson_sampler(lam):
+    k = _sample('poisson', a=lam, n=300000)
+    assert abs(k.mean() - lam) < 5 * np.sqrt(lam / k.size)
+    assert abs(k.var() / lam - 1) < 0.02
+    lo, hi = int(max(0, lam - 6 * np.sqrt(lam) - 2)), int(lam + 6 * np.sqrt(lam) + 3)
+    edges = np.arange(lo, hi + 1)
+    exp = sps.poisson.pmf(edges, lam) * k.size
+    keep = exp >= 8
+    obs = np.array([(k == e).sum() for e in edges[keep]], dtype=float)
+    obs = np.append(obs, k.size - obs.sum())
+    exp = np.append(exp[keep], k.size - exp[keep].sum())
+    ok = exp > 0
+    chi2 = ((obs[ok] - exp[ok]) ** 2 / exp[ok]).sum()
+    assert sps.chi2.sf(chi2, ok.sum() - 1) > 1e-4, (lam, chi2, ok.sum())
+
+
+@pytest.mark.parametrize('n0,xt', [(1, 0.08), (7, 0.1), (100, 0.08), (3000, 0.3)])
+def test_branching_total_is_generalised_poisson(n0, xt):
+    s = _sample('branching', a=xt, b=n0, n=200000)
+    mean, var = n0 / (1 - xt), n0 * xt / (1 - xt) ** 3
+    assert abs(s.mean() - mean) < 5 * np.sqrt(var / s.size)
+    assert abs(s.var() / var - 1) < 0.03
+    if n0 == 1:   # a single tree is Borel
+        pmf = orc.borel_pmf(xt, 50)
+        obs = np.bincount(s.astype(int), minlength=8)[1:6]
+        assert np.all(np.abs(obs - pmf[:5] * s.size) < 5 * np.sqrt(pmf[:5] * s.size) + 1)
+
+
+# ------------------------------------------------------------------ moments vs closed form
+def _moment_check(kw, n_events, kernel='auto', var_tol=0.03):
+    P = kw['n_pixels']
+    g = gen(seed=77, kernel=kernel, saturate=None, **kw)
+    c = cube(g, n_events).astype(np.float64)                    # (E,P,B)
+    cfg = orc.make_config(**kw)
+    mean, var = orc.closed_form_moments(cfg)
+    m_hat, v_hat = c.mean(axis=0), c.var(axis=0)
+    z = (m_hat - mean) / np.sqrt(var / n_events)
+    assert np.abs(z).max() < 6, 'per-(pixel,bin) mean off by %.1f sigma' % np.abs(z).max()
+    assert abs(z.mean()) < 6 / np.sqrt(z.size)
+    # pooled over pixels with identical parameters the variance is sharp
+    if np.ptp(cfg.nsb_rate) == 0 and np.ptp(cfg.n_photon) == 0:
+        ratio = v_hat.mean(axis=0) / var.mean(axis=0)
+        assert np.abs(ratio - 1).max() < var_tol, ratio
+    return g, c, cfg
+
+
+def test_moments_dark_run():
+    _moment_check(dict(n_pixels=64, n_photon=0, **DARK), 4000)
+
+
+@pytest.mark.parametrize('rate', [0.04, 0.66, 1.0])
+@pytest.mark.parametrize('kernel', ['scatter', 'sweep'])
+def test_moments_nsb_levels(rate, kernel):
+    _moment_check(dict(n_pixels=64, nsb_rate=rate, n_photon=0., **ACDC), 3000, kernel=kernel)
+
+
+def test_moments_with_signal_pulse_and_edge_effect():
+    g, c, cfg = _moment_check(dict(n_pixels=32, nsb_rate=1.0, n_photon=10., **ACDC), 6000, var_tol=0.05)
+    m = c.mean(axis=(0, 1))
+    # NSB only exists from -40 ns, the template is 88 ns long: early bins sit below true_baseline
+    assert m[0] < g.true_baseline[0] - 1.0
+    assert abs(m[-1] - g.true_baseline[0]) < 0.5
+
+
+def test_moments_per_pixel_arrays_and_lowgain_template():
+    kw = dict(n_pixels=5, nsb_rate=[0.0, 0.05, 0.2, 0.6, 1.2], crosstalk=[0.0, 0.05, 0.1, 0.2, 0.3],
+              sigma_e=[0.5, 0.8, 1.0, 1.5, 2.0], sigma_1=[0.0, 0.4, 0.8, 1.0, 1.2],
+              gain=[4., 5., 5.8, 6., 7.], baseline=[100, 200, 300, 400, 10],
+              n_photon=[[0.], [3.], [30.], [300.], [1.]],
+              time_signal=[[10.], [20.], [30.], [40.], [-20.]],
+              jitter=[[0.], [0.5], [1.], [2.], [4.]], gain_nsb=0.7)
+    _moment_check(kw, 20000)
+    kw = dict(n_pixels=8, nsb_rate=0.5, gain_nsb=1 / 0.85, gain=5.8, baseline=500, sigma_e=0.8,
+              sigma_1=0.8, crosstalk=0.08, time_end=200,
+              pulse_shape_file='utils/pulse_SST-1M_AfterPreampLowGain.dat')
+    _moment_check(kw, 8000)
+
+
+def test_moments_sub_binning_and_dt2():
+    _moment_check(dict(n_pixels=16, time_start=0, time_end=100, time_sampling=2, nsb_rate=0.2), 8000)
+    # on-grid NSB: compare with the oracle's own sampling (no closed form for the grid process here)
+    kw = dict(n_pixels=16, nsb_rate=0.3, sub_binning=1, n_photon=4)
+    g = gen(seed=5, saturate=None, **kw)
+    c = cube(g, 6000).astype(np.float64)
+    cfg = orc.make_config(**kw)
+    rng = np.random.RandomState(3)
+    o = np.stack([orc.next_event(cfg, rng).adc_float for _ in range(400)])
+    se = np.sqrt(o.var(axis=(0, 1)) / (o.shape[0] * o.shape[1]) + c.var(axis=(0, 1)) / (c.shape[0] * c.shape[1]))
+    assert np.abs((c.mean(axis=(0, 1)) - o.mean(axis=(0, 1))) / se).max() < 5
+    assert np.abs(c.var(axis=(0, 1)) / o.var(axis=(0, 1)) - 1).max() < 0.12
+
+
+# ------------------------------------------------------------------ two-sample tests vs the oracle
+@pytest.mark.parametrize('kw,n_oracle', [
+    (dict(n_pixels=48, nsb_rate=0.125, n_photon=10., **ACDC), 60),
+    (dict(n_pixels=48, n_photon=2, **DARK), 120),
+])
+def test_adc_and_charge_histograms_match_oracle(kw, n_oracle):
+    g = gen(seed=2024, **kw)
+    adc, t, q = cube(g, 4000, truth=True)
+    cfg = orc.make_config(**kw)
+    rng = np.random.RandomState(8)
+    recs = [orc.next_event(cfg, rng) for _ in range(n_oracle)]
+    o_adc = np.stack([orc.saturate(r.adc_float) for r in recs])
+    o_q = np.stack([np.asarray(r.sig_amplitude, dtype=float) for r in recs])
+    # ADC spectrum: chi2 two-sample on bins with enough oracle entries
+    lo, hi = int(min(adc.min(), o_adc.min())), int(max(adc.max(), o_adc.max()))
+    h_g = np.bincount(adc.ravel() - lo, minlength=hi - lo + 1).astype(float)
+    h_o = np.bincount(o_adc.ravel() - lo, minlength=hi - lo + 1).astype(float)
+    keep = h_o >= 25
+    k1, k2 = np.sqrt(h_o[keep].sum() / h_g[keep].sum()), np.sqrt(h_g[keep].sum() / h_o[keep].sum())
+    chi2 = ((k1 * h_g[keep] - k2 * h_o[keep]) ** 2 / (h_g[keep] + h_o[keep])).sum()
+    # samples inside a trace are correlated (shared pe), so the effective dof is inflated: tolerance 2x
+    assert chi2 < 2.0 * keep.sum() + 6 * np.sqrt(2 * keep.sum()), (chi2, keep.sum())
+    # signal charge: KS two-sample (independent across traces)
+    assert sps.ks_2samp(q.ravel(), o_q.ravel()).pvalue > 1e-3
+    # signal time: uniform jitter around time_signal
+    j = cfg.jitter[0, 0]
+    assert t.min() >= cfg.time_signal[0, 0] - j / 2 - 1e-4 and t.max() <= cfg.time_signal[0, 0] + j / 2 + 1e-4
+    assert sps.kstest((t.ravel() - cfg.time_signal[0, 0]) / j + 0.5, 'uniform').pvalue > 1e-3
+
+
+# ------------------------------------------------------------------ saturation, edge cases
+def test_twelve_bit_saturation_on_c4():
+    P = 1296
+    npe = [[float(10 ** (3.5 * i / (P - 1)))] for i in range(P)]
+    g = gen(n_pixels=P, nsb_rate=1.0, n_photon=npe, seed=20261019, **ACDC)
+    assert g.kernel == 'sweep'
+    c = cube(g, 16)
+    assert c.min() >= 0 and c.max() == 4095
+    peak = c.max(axis=2).mean(axis=0)
+    assert np.all(peak[-60:] == 4095) and np.all(peak[:600] < 4095)
+    # unsaturated build shows what was clipped
+    g2 = gen(n_pixels=P, nsb_rate=1.0, n_photon=npe, seed=20261019, saturate=None, **ACDC)
+    c2 = cube(g2, 16)
+    assert c2.max() > 4095 and np.array_equal(np.clip(c2, 0, 4095), c)
+
+
+def test_negative_values_clamp_to_zero():
+    g = gen(n_pixels=8, baseline=0, nsb_rate=0.01, sigma_e=2.0, n_photon=0, seed=4)
+    c = cube(g, 200)
+    assert c.min() == 0 and (c == 0).mean() > 0.2
+
+
+def test_degenerate_configs():
+    # nothing random at all: every sample equals round(baseline)
+    g = gen(n_pixels=3, nsb_rate=0, crosstalk=0, sigma_e=0, sigma_1=0, n_photon=0, baseline=[10, 20.4, 30.6])
+    c = cube(g, 5)
+    assert np.array_equal(c[:, 0], np.full((5, 50), 10)) and np.all(c[:, 1] == 20) and np.all(c[:, 2] == 31)
+    # deterministic pulse: poisson off, no crosstalk, no smearing -> analytic trace, incl. t on a sample
+    g = gen(n_pixels=2, nsb_rate=0, crosstalk=0, sigma_e=0, sigma_1=0, n_photon=50, poisson=False,
+            gain_nsb=False, gain=5.0, baseline=100, time_signal=20, jitter=0)
+    c = cube(g, 3)
+    t = np.arange(0, 200, 4)
+    want = np.round(100 + 5.0 * 50 * g.get_pulse_shape(t, t_0=20)).astype(int)
+    assert np.abs(c[0, 0] - want).max() <= 1 and (c[0, 0] != want).sum() <= 1
+    assert want[5] > 100                                          # h(0) > 0 counted at t == time_signal
+    # zero events / one pixel / odd bin count
+    assert cube(g, 0).shape == (0, 2, 50)
+    g = gen(n_pixels=1, time_end=199, nsb_rate=0.3, seed=1)
+    assert cube(g, 3).shape == (3, 1, 50)
+    g = gen(n_pixels=5, time_start=0, time_end=102, time_sampling=6, nsb_rate=0.3, seed=1)   # dt not a multiple of the knot step? 6/0.5=12 phases
+    assert cube(g, 3).shape[2] == g.params.n_bins
+
+
+# ------------------------------------------------------------------ iterator semantics (reference tests)
+def test_n_events_like_reference_test():
+    for n in (0, 1, 10, 100):                                     # test_NTraceGenerator.py:4-13
+        toy = gen(nsb_rate=0.000001, n_events=n, n_pixels=16)
+        assert len([e for e in toy]) == n
+
+
+def test_sampling_like_reference_test():
+    param = {'time_start': 0, 'time_end': 100, 'time_sampling': 2}   # test.py:7-13
+    toy = gen(n_pixels=4, **param)
+    toy.next()
+    assert toy.adc_count.shape[-1] == (param['time_end'] - param['time_start']) // param['time_sampling']
+
+
+def test_iterator_surface():
+    toy = gen(n_pixels=3, baseline=[0, 500, 0], n_photon=[[100, 133], [60, 60, 60], [100, 133]],
+              time_signal=[[0, 100], [20, 50, 100], [0, 100]], gain=[10, 10, 29], poisson=True,
+              n_events=5, seed=1, batch_events=2, pulse_shape_file='utils/pulse_SST-1M_pixel_0.dat',
+              some_unknown_option=1)                              # example.py:8-12; extra kwargs ignored
+    assert iter(toy) is toy and toy.count == -1
+    assert toy.adc_count.shape == (3, 60) and not toy.adc_count.any()    # before the first event (:199)
+    seen = []
+    for ev in toy:
+        assert ev is toy
+        assert ev.adc_count.shape == (3, 50) and ev.cherenkov_time.shape == (3, 3)
+        assert ev.cherenkov_photon.shape == (3, 3) and ev.cherenkov_photon[0, 2] == 0
+        assert ev.sampling_bins.shape == (50,) and ev.sampling_bins[0] == 0
+        seen.append((ev.count, np.array(ev.adc_count)))
+    assert [s[0] for s in seen] == [0, 1, 2, 3, 4]
+    bulk = cube(gen(n_pixels=3, baseline=[0, 500, 0], n_photon=[[100, 133], [60, 60, 60], [100, 133]],
+                    time_signal=[[0, 100], [20, 50, 100], [0, 100]], gain=[10, 10, 29], seed=1), 5)
+    assert all(np.array_equal(s[1], bulk[i]) for i, s in enumerate(seen))   # batching is invisible
+    with pytest.raises(AttributeError):
+        toy.nsb_time
+    assert toy.true_baseline.shape == (3,) and toy.tau > 17
+
+
+# ------------------------------------------------------------------ K3 statistics kernel
+def test_stats_kernel_matches_numpy():
+    import torch
+    g = gen(n_pixels=50, nsb_rate=0.3, n_photon=5., seed=9, **ACDC)
+    out = g.generate(300)
+    from digicamtoy_b200.stats import CubeStats
+    st = CubeStats(g, charge_lo=-500, n_charge_bins=4000)
+    st.accumulate(out[:100])
+    st.accumulate(out[100:])
+    r = st.result()
+    c = out.cpu().numpy().astype(np.int64)
+    assert np.array_equal(r['adc_hist'], np.bincount(c.ravel(), minlength=4096))
+    assert np.allclose(r['bin_sum'], c.sum(axis=(0, 1))) and np.allclose(r['bin_sumsq'], (c ** 2).sum(axis=(0, 1)))
+    assert np.allclose(r['pixel_sum'], c.sum(axis=(0, 2))) and np.allclose(r['pixel_sumsq'], (c ** 2).sum(axis=(0, 2)))
+    charge = c.sum(axis=2) - 50 * 280
+    assert np.array_equal(r['charge_hist'], np.bincount(np.clip(charge.ravel() + 500, 0, 3999), minlength=4000))
+    x = c.ravel().astype(np.float64)
+    assert np.allclose(r['moments'], [x.sum(), (x ** 2).sum(), (x ** 3).sum(), (x ** 4).sum()], rtol=1e-12)
+    mean, mean_err, std, std_err = st.moments_nsb()
+    assert mean == pytest.approx(x.mean()) and std == pytest.approx(x.std())
+
+
+def test_write_calibrate_kernel():
+    import torch
+    from digicamtoy_b200 import native
+    buf = torch.full((1 << 20) + 3, -1, dtype=torch.int16, device='cuda')
+    native.write_calibrate(buf.data_ptr(), buf.numel())
+    torch.cuda.synchronize()
+    assert int((buf < 0).sum()) == 0
