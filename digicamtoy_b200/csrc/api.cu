@@ -205,20 +205,29 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         p.n_phase = (int)nph;
         p.n_taps = (n_iv + p.n_phase - 1) / p.n_phase;
     }
+    p.phase_cap = 8388608.0f + (float)std::max(0, p.n_phase - 1);
     // on-grid taps
     const int m_lo = (int)std::ceil(x_lo / c->dt - 1e-9), m_hi = (int)std::floor(x_hi / c->dt + 1e-9);
     p.grid_m_lo = m_lo; p.grid_n = std::max(0, m_hi - m_lo + 1);
 
     // ---- host staging of every device array
-    std::vector<float> f_rate(P), f_inv(P), f_xt(P), f_exp(P), f_gain(P), f_s1(P), f_se(P), f_base(P);
+    std::vector<float> f_rate(P), f_inv(P), f_xt(P), f_exp((size_t)P * 4), f_gain(P), f_s1(P), f_se(P), f_base(P);
     std::vector<double> d_gain(P), d_base(P);
     std::vector<float> f_npe((size_t)P * K), f_tsig((size_t)P * K), f_jit((size_t)P * K);
     double pe_sum = 0.0;
     for (int i = 0; i < P; ++i) {
         f_rate[i] = (float)c->nsb_rate[i];
-        f_inv[i] = c->nsb_rate[i] > 0.0 ? (float)(1.0 / c->nsb_rate[i]) : 0.0f;
+        f_inv[i] = c->nsb_rate[i] > 0.0 ? (float)(-0.6931471805599453 / c->nsb_rate[i]) : 0.0f;
         f_xt[i] = (float)c->crosstalk[i];
-        f_exp[i] = (float)std::exp(-c->crosstalk[i]);
+        {   // Borel(mu): P(1) = e^-mu, P(n+1)/P(n) = mu e^-mu (1+1/n)^(n-1)
+            const double mu = c->crosstalk[i];
+            double pn = std::exp(-mu), cdf = pn;
+            for (int n = 1; n <= 4; ++n) {
+                f_exp[(size_t)i * 4 + (n - 1)] = (float)std::min(cdf, 1.0);
+                pn *= mu * std::exp(-mu) * std::pow(1.0 + 1.0 / n, n - 1.0);
+                cdf += pn;
+            }
+        }
         f_gain[i] = (float)c->gain[i];
         f_s1[i] = (float)c->sigma_1[i];
         f_se[i] = (float)c->sigma_e[i];
@@ -249,7 +258,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     // ---- one arena
     size_t cur = 0;
     const size_t o_rate = arena_reserve<float>(cur, P), o_inv = arena_reserve<float>(cur, P),
-                 o_xt = arena_reserve<float>(cur, P), o_exp = arena_reserve<float>(cur, P),
+                 o_xt = arena_reserve<float>(cur, P), o_exp = arena_reserve<float>(cur, (size_t)P * 4),
                  o_gain = arena_reserve<float>(cur, P), o_s1 = arena_reserve<float>(cur, P),
                  o_se = arena_reserve<float>(cur, P), o_base = arena_reserve<float>(cur, P),
                  o_dgain = arena_reserve<double>(cur, P), o_dbase = arena_reserve<double>(cur, P),
@@ -285,8 +294,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         delete h;
         return fail(DCT_E_CUDA, "parameter upload failed: %s", cudaGetErrorString(ue));
     }
-    p.rate = (const float*)(base + o_rate); p.inv_rate = (const float*)(base + o_inv);
-    p.xt = (const float*)(base + o_xt); p.exp_neg_xt = (const float*)(base + o_exp);
+    p.rate = (const float*)(base + o_rate); p.neg_ln2_over_rate = (const float*)(base + o_inv);
+    p.xt = (const float*)(base + o_xt); p.borel_cdf = (const float4*)(base + o_exp);
     p.gain = (const float*)(base + o_gain); p.sigma1 = (const float*)(base + o_s1);
     p.sigma_e = (const float*)(base + o_se); p.baseline = (const float*)(base + o_base);
     p.gain_d = (const double*)(base + o_dgain); p.baseline_d = (const double*)(base + o_dbase);

@@ -23,6 +23,7 @@ struct DevParams {
     float off0;                   // x_lo - cell0*dt  in [0, dt)
     // polyphase float32 table: tap j, phase f -> interval f + n_phase*j   (valid if n_phase > 0)
     int n_phase, n_taps;
+    float phase_cap;              // 2^23 + n_phase - 1 (see phase_of)
     // on-grid taps for sub_binning > 0: h(m*dt), m = grid_m_lo .. grid_m_lo + grid_n - 1
     int grid_m_lo, grid_n;
     // double precision copies for the replay kernels
@@ -30,9 +31,9 @@ struct DevParams {
 
     // per-pixel float32 SoA, [P]
     const float* rate;            // GHz
-    const float* inv_rate;        // ns (0 where rate == 0)
+    const float* neg_ln2_over_rate;  // -ln2 / rate [ns] (0 where rate == 0): gap = lg2(u) * this
     const float* xt;
-    const float* exp_neg_xt;
+    const float4* borel_cdf;      // P(n<=1), P(n<=2), P(n<=3), P(n<=4) of Borel(xt)
     const float* gain;
     const float* sigma1;          // relative
     const float* sigma_e;

@@ -2,7 +2,7 @@
 //
 // One thread owns one (event, pixel) trace.  A CTA owns NT consecutive traces of the
 // [event][pixel][bin] cube, i.e. one contiguous run of NT*B int16 in HBM, which it writes with
-// 16-byte stores from a shared-memory staging buffer.
+// 16-byte streaming stores gathered from shared memory.
 //
 // Stages per trace (reference digicamtoy/tracegenerator/__init__.py, `next` :201-226):
 //   NSB photo-electrons    generate_nsb :240-257      Poisson process by exponential gaps
@@ -12,6 +12,10 @@
 //   signal pulses          add_signal_photon :228-238
 //   electronic noise       generate_electronic_smearing :364-371  kept bins only
 //   digitisation           convert_to_digital :373-381  + 12-bit saturation (new)
+//
+// Shared memory: every trace has a private row of SB = (B | 1) floats (odd stride: lanes that touch
+// the same bin hit 32 different banks).  The analog sums accumulate there; digitisation then packs
+// the int16 result into the front of the same row, so no second staging buffer is needed.
 #pragma once
 #include "device_params.cuh"
 #include "sampling.cuh"
@@ -20,8 +24,14 @@ namespace dct {
 
 constexpr int GEN_THREADS = 128;        // default traces per CTA; 32 for very long traces
 
-// shaping arithmetic shared by every float32 path (stochastic kernels and replay_f32); explicit
-// intrinsics so that no two kernels contract it differently.
+__host__ __device__ inline int row_stride(int B) { return B | 1; }
+
+__host__ __device__ inline size_t gen_smem_bytes(int B, int n_table_entries, int nt) {
+    return (size_t)n_table_entries * 16 + (size_t)nt * row_stride(B) * sizeof(float);
+}
+
+// shaping arithmetic shared by every float32 path; explicit intrinsics so that no two kernels
+// contract it differently (the sweep and scatter kernels must agree bit for bit).
 __device__ __forceinline__ float horner(const float4 c, float u) {
     return __fmaf_rn(__fmaf_rn(__fmaf_rn(c.w, u, c.z), u, c.y), u, c.x);
 }
@@ -36,12 +46,14 @@ __device__ __forceinline__ float template_at(const DevParams& p, const float4* c
     return horner(coef[m], u);
 }
 
-// Digitise one sample: analog sum -> LSB.  Same operation order as the reference
-// (x gain :362, + noise :371, + baseline :379, round half-to-even :380), then saturate.
+// Digitise one sample: analog sum -> LSB.  Same operation order as the reference (x gain :362,
+// + noise :371, + baseline :379, round half-to-even :380), then saturate.  The rounding is the
+// float add of 1.5*2^23 (round-to-nearest-even in hardware, FMA pipe) instead of an F2I (XU pipe).
 __device__ __forceinline__ int digitise(float acc, float gain, float noise, float baseline,
-                                        int lo, int hi) {
-    const float v = __fadd_rn(__fadd_rn(__fmul_rn(acc, gain), noise), baseline);
-    return max(lo, min(hi, __float2int_rn(v)));
+                                        float lo, float hi) {
+    float v = __fadd_rn(__fadd_rn(__fmul_rn(acc, gain), noise), baseline);
+    v = fminf(fmaxf(v, lo), hi);
+    return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
 }
 
 struct GenArgs {
@@ -54,40 +66,6 @@ struct GenArgs {
     float* sig_charge;
     int table_in_smem;          // generic coef32 table staged in shared memory
 };
-
-// Dynamic shared memory layout (floats then halves):
-//   V    [B][NT] float   analog accumulators of the kept bins, thread-minor => conflict-free
-//   tab  float4[...]     polyphase table (or generic table)
-//   out  [NT*B] int16    dense staging of the CTA's output run
-__host__ __device__ inline size_t gen_smem_bytes(int B, int n_table_entries, int nt) {
-    size_t v = (size_t)B * nt * sizeof(float);
-    size_t t = (size_t)n_table_entries * 16;
-    size_t o = ((size_t)nt * B * sizeof(int16_t) + 15) & ~(size_t)15;
-    return v + t + o;
-}
-
-// Generic version: onset y0 in [0, dt) before... i.e. bin `first_bin` sees template argument y0,
-// the next one y0 + dt, ...  Inclusive at y == L.  Used for signal pulses (which may sit exactly
-// on a sample) and for templates whose knot spacing does not divide the sampling period.
-template <int NT>
-__device__ __forceinline__ void scatter_generic(const DevParams& p, const float4* coef, float* V,
-                                                int first_bin, float y0, float A) {
-    const int kb = first_bin - p.n_drop;
-    int j = max(0, -kb);
-    for (;; ++j) {
-        const float y = __fmaf_rn((float)j, p.dt, y0);
-        if (y > p.L || kb + j >= p.B) break;
-        const float h = template_at(p, coef, y);
-        float* v = V + (kb + j) * NT;
-        *v = __fmaf_rn(A, h, *v);
-    }
-}
-
-__device__ __forceinline__ float smeared_amplitude(int n, float z, float sigma1) {
-    // A = n + N(0, sqrt(n) sigma_1 / gain)   (:331-348); zero spread -> exactly n
-    const float fn = (float)n;
-    return __fmaf_rn(z * sigma1, sqrtf(fn), fn);
-}
 
 // Identity of the trace a thread owns.
 struct TraceId {
@@ -110,34 +88,70 @@ __device__ __forceinline__ TraceId trace_id(const GenArgs& a, uint64_t g) {
 
 // Moves the onset (cell*dt + off) forward by one exponential gap; returns how many cell
 // boundaries were crossed.  Shared by both kernels so that they place every pe identically.
+// The common cases (0 or 1 crossing) are predicated; long gaps take the floor path.
 __device__ __forceinline__ int advance_onset(const DevParams& p, float gap, int& cell, float& off) {
     off += gap;
-    if (off < p.dt) return 0;
-    const float kf = floorf(off * p.inv_dt);
-    int k = (int)kf;
-    off = fmaxf(__fmaf_rn(-kf, p.dt, off), 0.0f);
-    if (off >= p.dt) { off -= p.dt; ++k; }
+    int k = 0;
+    if (off >= p.dt) {
+        off -= p.dt;
+        k = 1;
+        if (off >= p.dt) {
+            const float kf = floorf(off * p.inv_dt);
+            off = fmaxf(__fmaf_rn(-kf, p.dt, off), 0.0f);
+            k += (int)kf;
+            if (off >= p.dt) { off -= p.dt; ++k; }
+        }
+    }
     cell += k;
     return k;
 }
 
-// Phase (which knot interval of the first tap) and local offset of a pe that lies x0 before a bin.
+// Phase f (knot interval of the first tap) and local offset u of a pe that lies x0 in (0, dt]
+// before a bin.  floor() by a round-toward-zero add of 2^23: FMA pipe, no F2I / I2F.
 __device__ __forceinline__ void phase_of(const DevParams& p, float x0, int& f, float& u) {
-    f = min((int)(x0 * p.inv_knot_dx), p.n_phase - 1);
-    u = x0 - (float)f * p.knot_dx;
+    float r = __fadd_rz(x0 * p.inv_knot_dx, 8388608.0f);
+    r = fminf(r, p.phase_cap);                       // 2^23 + n_phase - 1  (x0 == dt -> last phase)
+    f = __float_as_int(r) & 0x7f;
+    u = __fmaf_rn(8388608.0f - r, p.knot_dx, x0);    // x0 - f * knot_dx
 }
 
-// One NSB photo-electron cluster from its Philox block: amplitude after crosstalk and smearing.
-__device__ __forceinline__ float nsb_amplitude(const u32x4& r, float xt, float exp_neg_xt, float sigma1) {
-    const int n = borel(r.y, xt, exp_neg_xt);
-    return (sigma1 > 0.0f) ? smeared_amplitude(n, normal_one(r.z, r.w), sigma1) : (float)n;
+// Per-pixel constants of the NSB photo-electron stream.
+struct PixelNsb {
+    float neg_ln2_over_rate;   // -ln2 / rate
+    float xt;
+    float4 borel_cdf;
+    float sigma1;              // relative gain spread
+};
+
+// One NSB photo-electron cluster from its Philox block: amplitude after crosstalk (:297-327) and
+// gain smearing (:329-348):  A = n + sigma_1 sqrt(n) z.
+__device__ __forceinline__ float nsb_amplitude(const u32x4& r, const PixelNsb& q) {
+    const float fn = (float)borel(r.y, q.xt, q.borel_cdf);
+    return __fmaf_rn(q.sigma1, normal_scaled(r.z, r.w, fn), fn);
+}
+
+__device__ __forceinline__ float smeared_amplitude(int n, float z, float sigma1) {
+    const float fn = (float)n;
+    return __fmaf_rn(z * sigma1, fast_sqrt(fn), fn);
+}
+
+// Generic shaping of one cluster: bin `first_bin` (simulated index) sees template argument y0, the
+// next one y0 + dt, ...  Inclusive at y == L.  Used for signal pulses (which may sit exactly on a
+// sample) and for templates whose knot spacing does not divide the sampling period.
+__device__ __forceinline__ void scatter_generic(const DevParams& p, const float4* coef, float* row,
+                                                int first_bin, float y0, float A) {
+    const int kb = first_bin - p.n_drop;
+    for (int j = max(0, -kb);; ++j) {
+        const float y = __fmaf_rn((float)j, p.dt, y0);
+        if (y > p.L || kb + j >= p.B) break;
+        row[kb + j] = __fmaf_rn(A, template_at(p, coef, y), row[kb + j]);
+    }
 }
 
 // Signal pulses of one trace (add_signal_photon :228-238 + their crosstalk :319-324 + smearing),
-// shaped into the accumulators V; optional truth outputs (cherenkov_time / cherenkov_photon).
-template <int NT>
+// shaped into the accumulators; optional truth outputs (cherenkov_time / cherenkov_photon).
 __device__ __forceinline__ void add_signal_pulses(const GenArgs& a, const TraceId& t, const float4* coef,
-                                                  float* V, float xt, float sigma1) {
+                                               float* row, float xt, float sigma1) {
     const DevParams& p = a.p;
     for (int k = 0; k < p.K; ++k) {
         const float npe = p.npe[t.pixel * p.K + k];
@@ -161,19 +175,21 @@ __device__ __forceinline__ void add_signal_pulses(const GenArgs& a, const TraceI
             float y0 = __fmaf_rn((float)b1, p.dt, -s);
             if (y0 < 0.0f) { y0 += p.dt; ++b1; }
             if (y0 >= p.dt) { y0 -= p.dt; --b1; }
-            scatter_generic<NT>(p, coef, V, b1, y0, A);
+            scatter_generic(p, coef, row, b1, y0, A);
         }
     }
 }
 
-// Electronic noise (kept bins only) + digitisation of one trace into its row of the staging run.
-template <int NT>
-__device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId& t, const float* V,
-                                               int16_t* row) {
+// Electronic noise (kept bins only) + digitisation of one trace, in place: the int16 results are
+// packed into the front of the trace's own float row (sample b -> half-word b).  Reading runs
+// ahead of writing (word b/2 <= b), so nothing unread is overwritten.
+__device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId& t, float* row) {
     const float gain = p.gain[t.pixel];
     const float sigma_e = p.sigma_e[t.pixel];
     const float baseline = p.baseline[t.pixel];
+    const float lo = (float)p.adc_min, hi = (float)p.adc_max;
     const int B = p.B;
+    uint32_t* packed = reinterpret_cast<uint32_t*>(row);
     for (int q = 0; 4 * q < B; ++q) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (sigma_e > 0.0f) {
@@ -181,46 +197,79 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId
             normal_pair(r.x, r.y, z[0], z[1]);
             normal_pair(r.z, r.w, z[2], z[3]);
         }
+        const int b = 4 * q;
+        int d[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int b = 4 * q + i;
-            if (b < B)
-                row[b] = (int16_t)digitise(V[b * NT], gain, z[i] * sigma_e, baseline, p.adc_min, p.adc_max);
+        for (int i = 0; i < 4; ++i)
+            d[i] = (b + i < B) ? digitise(row[b + i], gain, z[i] * sigma_e, baseline, lo, hi) : 0;
+        packed[2 * q] = (uint32_t)(d[0] & 0xffff) | ((uint32_t)d[1] << 16);
+        if (b + 2 < B) packed[2 * q + 1] = (uint32_t)(d[2] & 0xffff) | ((uint32_t)d[3] << 16);
+    }
+}
+
+// Coalesced store of the CTA's contiguous run of the cube: 16-byte streaming stores gathered from
+// the packed rows.  Output 32-bit word w of the run lives in row w / (B/2), word w % (B/2).
+template <int NT>
+__device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const float* rows) {
+    const int tid = threadIdx.x;
+    const int B = a.p.B, SB = row_stride(B);
+    const uint64_t left = a.n_traces - trace0;
+    const int n_live = (int)(left < (uint64_t)NT ? left : (uint64_t)NT);
+    int16_t* dst = a.adc + trace0 * (uint64_t)B;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(rows);
+    if ((B & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int wpr = B >> 1;                                   // words per row
+        const int n_words = n_live * wpr;
+        const int n_vec = n_words >> 2;
+        const float inv_wpr = 1.0f / (float)wpr;
+        int4* dst4 = reinterpret_cast<int4*>(dst);
+        for (int v = tid; v < n_vec; v += NT) {
+            const int w0 = 4 * v;
+            int r = (int)(((float)w0 + 0.5f) * inv_wpr);          // exact: w0 < 2^16
+            int c = w0 - r * wpr;
+            int x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] = (int)words[r * SB + c];
+                if (++c == wpr) { c = 0; ++r; }
+            }
+            __stcs(dst4 + v, make_int4(x[0], x[1], x[2], x[3]));
+        }
+        uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);
+        for (int w = 4 * n_vec + tid; w < n_words; w += NT) {
+            const int r = w / wpr;
+            dst32[w] = words[r * SB + (w - r * wpr)];
+        }
+    } else {
+        const int16_t* halves = reinterpret_cast<const int16_t*>(rows);
+        const int n_el = n_live * B;
+        for (int e = tid; e < n_el; e += NT) {
+            const int r = e / B;
+            dst[e] = halves[r * SB * 2 + (e - r * B)];
         }
     }
 }
 
-// Coalesced store of the CTA's contiguous run of the cube: 16-byte streaming stores.
-template <int NT>
-__device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const int16_t* out_s) {
-    const int tid = threadIdx.x;
-    const uint64_t left = a.n_traces - trace0;
-    const size_t n_el = (size_t)(left < (uint64_t)NT ? left : (uint64_t)NT) * a.p.B;
-    int16_t* dst = a.adc + trace0 * (uint64_t)a.p.B;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        const size_t n_vec = n_el / 8;
-        const int4* src4 = reinterpret_cast<const int4*>(out_s);
-        int4* dst4 = reinterpret_cast<int4*>(dst);
-        for (size_t i = tid; i < n_vec; i += NT) __stcs(dst4 + i, src4[i]);
-        for (size_t i = n_vec * 8 + tid; i < n_el; i += NT) dst[i] = out_s[i];
-    } else {
-        for (size_t i = tid; i < n_el; i += NT) dst[i] = out_s[i];
-    }
+__device__ __forceinline__ PixelNsb load_pixel_nsb(const DevParams& p, int pixel) {
+    PixelNsb q;
+    q.neg_ln2_over_rate = p.neg_ln2_over_rate[pixel];
+    q.xt = p.xt[pixel];
+    q.borel_cdf = p.borel_cdf[pixel];
+    q.sigma1 = p.sigma1[pixel];
+    return q;
 }
 
 template <bool POLY, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 1))
 k_generate_scatter(const GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& p = a.p;
     const int tid = threadIdx.x;
     const int B = p.B;
 
-    float* Vall = reinterpret_cast<float*>(smem_raw);
     const int n_tab = POLY ? p.n_taps * p.n_phase : (a.table_in_smem ? p.n_iv : 0);
-    float4* tab_s = reinterpret_cast<float4*>(smem_raw + (size_t)B * NT * sizeof(float));
-    int16_t* out_s = reinterpret_cast<int16_t*>(tab_s + n_tab);
-
+    float4* tab_s = reinterpret_cast<float4*>(smem_raw);
+    float* rows = reinterpret_cast<float*>(tab_s + n_tab);
     {   // stage the template table
         const float4* src = POLY ? p.poly : p.coef32;
         for (int i = tid; i < n_tab; i += NT) tab_s[i] = src[i];
@@ -228,48 +277,42 @@ k_generate_scatter(const GenArgs a) {
     // generic coefficient table: shared copy if it fits, else straight from global (L1/L2)
     const float4* coef_g = (!POLY && a.table_in_smem) ? tab_s : p.coef32;
 
-    float* V = Vall + tid;
-    for (int b = 0; b < B; ++b) V[b * NT] = 0.0f;
+    float* row = rows + tid * row_stride(B);
+    for (int b = 0; b < B; ++b) row[b] = 0.0f;
     __syncthreads();
 
     const uint64_t trace0 = (uint64_t)blockIdx.x * NT;
     if (trace0 + tid < a.n_traces) {
         const TraceId t = trace_id(a, trace0 + tid);
         const float rate = p.rate[t.pixel];
-        const float xt = p.xt[t.pixel];
-        const float exp_neg_xt = p.exp_neg_xt[t.pixel];
-        const float sigma1 = p.sigma1[t.pixel];
+        const PixelNsb q = load_pixel_nsb(p, t.pixel);
 
         if (rate > 0.0f) {
             if (p.sub_binning <= 0) {
                 // Poisson process on [t0, t_end): exponential gaps.  Same law as the reference's
                 // Poisson count + iid uniform times (:244-250) without padding to max_photon.
-                const float inv_rate = p.inv_rate[t.pixel];
                 float elapsed = 0.0f;
                 int cell = p.cell0;
                 float off = p.off0;                                   // onset = cell*dt + off
                 for (uint32_t i = 0;; ++i) {
                     const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                    const float gap = exp_gap(r.x, inv_rate);
+                    const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
                     elapsed += gap;
                     if (elapsed >= p.span) break;
                     advance_onset(p, gap, cell, off);
-                    const float A = nsb_amplitude(r, xt, exp_neg_xt, sigma1);
+                    const float A = nsb_amplitude(r, q);
                     const float x0 = p.dt - off;                      // (0, dt]
                     if (POLY) {
                         int f; float u;
                         phase_of(p, x0, f, u);
                         const int kb = cell + 1 - p.n_drop;           // kept index of tap 0
                         const int j_hi = min(p.n_taps, B - kb);
-                        for (int j = max(0, -kb); j < j_hi; ++j) {
-                            const float h = horner(tab_s[j * p.n_phase + f], u);
-                            float* v = V + (kb + j) * NT;
-                            *v = __fmaf_rn(A, h, *v);
-                        }
+                        for (int j = max(0, -kb); j < j_hi; ++j)
+                            row[kb + j] = __fmaf_rn(A, horner(tab_s[j * p.n_phase + f], u), row[kb + j]);
                     } else {
                         // bin cell+1 sees y = x0.  A pe exactly on a sample is also seen by that
                         // sample at y = 0: probability ~2^-24 per pe, ignored by both kernels.
-                        scatter_generic<NT>(p, coef_g, V, cell + 1, x0, A);
+                        scatter_generic(p, coef_g, row, cell + 1, x0, A);
                     }
                 }
             } else {
@@ -280,27 +323,24 @@ k_generate_scatter(const GenArgs a) {
                 for (int bs = 0; bs < n_sim; ++bs) {
                     const int n = poisson(rd, lam);
                     if (n <= 0) continue;
-                    const int total = branching_total(rd, n, xt);
+                    const int total = branching_total(rd, n, q.xt);
                     float A = (float)total;
-                    if (sigma1 > 0.0f) {
+                    if (q.sigma1 > 0.0f) {
                         const uint32_t r0 = rd.next(), r1 = rd.next();
-                        A = smeared_amplitude(total, normal_one(r0, r1), sigma1);
+                        A = smeared_amplitude(total, normal_one(r0, r1), q.sigma1);
                     }
                     for (int m = 0; m < p.grid_n; ++m) {
                         const int kb = bs + p.grid_m_lo + m - p.n_drop;
-                        if (kb >= 0 && kb < B) {
-                            float* v = V + kb * NT;
-                            *v = __fmaf_rn(A, p.grid_tap[m], *v);
-                        }
+                        if (kb >= 0 && kb < B) row[kb] = __fmaf_rn(A, p.grid_tap[m], row[kb]);
                     }
                 }
             }
         }
-        add_signal_pulses<NT>(a, t, POLY ? p.coef32 : coef_g, V, xt, sigma1);
-        digitise_trace<NT>(p, t, V, out_s + tid * B);
+        add_signal_pulses(a, t, POLY ? p.coef32 : coef_g, row, q.xt, q.sigma1);
+        digitise_trace(p, t, row);
     }
     __syncthreads();
-    store_run<NT>(a, trace0, out_s);
+    store_run<NT>(a, trace0, rows);
 }
 
 }  // namespace dct

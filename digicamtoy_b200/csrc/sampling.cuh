@@ -5,41 +5,58 @@
 //                                            reference digicamtoy/utils/pdf.py:26-32)
 //   Poisson(n_photon) signal size + one Galton-Watson tree per primary (:236, :319-324)
 //   Gaussian gain smearing / electronic noise (:337, :342, :369)
+// Transcendentals are the single-instruction MUFU approximations (lg2 / sqrt / sin / cos .approx):
+// absolute errors ~1e-7..1e-6, far below the 2^-24 granularity of the uniforms feeding them.
 #pragma once
 #include "philox.cuh"
 
 namespace dct {
 
-// Box-Muller; both outputs are independent N(0,1).
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// angle in [-pi, pi) from 23 random bits: one FFMA, no I2F; best range of MUFU.SIN/COS
+__device__ __forceinline__ float random_angle(uint32_t r) {
+    return fmaf(__uint_as_float(0x3f800000u | (r >> 9)), 6.28318530718f, -9.42477796077f);
+}
+
+constexpr float NEG_2LN2 = -1.38629436112f;     // -2 ln 2 : -2 ln(u) = NEG_2LN2 * lg2(u)
+constexpr float NEG_LN2 = -0.69314718056f;
+
+// Box-Muller; both outputs are independent N(0, s2) where the variance scale s2 multiplies -2 ln u
+// under the root (lets callers fold sqrt(n) of the gain smearing into the same MUFU.SQRT).
 __device__ __forceinline__ void normal_pair(uint32_t r0, uint32_t r1, float& z0, float& z1) {
-    const float u = u01_open0(r0);
-    // angle in [-pi, pi): best accuracy range of the MUFU sin/cos; one FFMA, no I2F
-    const float ang = fmaf(__uint_as_float(0x3f800000u | (r1 >> 9)), 6.28318530718f, -9.42477796077f);
-    const float rad = sqrtf(-2.0f * __logf(u));
+    const float rad = fast_sqrt(fast_lg2(u01_open0(r0)) * NEG_2LN2);
     float s, c;
-    __sincosf(ang, &s, &c);
+    __sincosf(random_angle(r1), &s, &c);
     z0 = rad * c;
     z1 = rad * s;
 }
 
-__device__ __forceinline__ float normal_one(uint32_t r0, uint32_t r1) {
-    const float u = u01_open0(r0);
-    const float ang = fmaf(__uint_as_float(0x3f800000u | (r1 >> 9)), 6.28318530718f, -9.42477796077f);
-    return sqrtf(-2.0f * __logf(u)) * __cosf(ang);
+// One N(0, var_scale) draw: cos(angle) * sqrt(-2 var_scale ln u).
+__device__ __forceinline__ float normal_scaled(uint32_t r0, uint32_t r1, float var_scale) {
+    return fast_sqrt(fast_lg2(u01_open0(r0)) * (NEG_2LN2 * var_scale)) * __cosf(random_angle(r1));
 }
+__device__ __forceinline__ float normal_one(uint32_t r0, uint32_t r1) { return normal_scaled(r0, r1, 1.0f); }
 
-// Exponential inter-arrival time of a Poisson process with the given 1/rate.
-__device__ __forceinline__ float exp_gap(uint32_t r, float inv_rate) {
-    return -__logf(u01_open0(r)) * inv_rate;
+// Exponential inter-arrival time of a Poisson process; neg_ln2_over_rate = -ln2 / rate.
+__device__ __forceinline__ float exp_gap(uint32_t r, float neg_ln2_over_rate) {
+    return fast_lg2(u01_open0(r)) * neg_ln2_over_rate;
 }
 
 // Borel(mu) by inversion: P(1) = e^-mu, P(n+1)/P(n) = mu e^-mu (1+1/n)^(n-1).
-// exp_neg_mu = e^-mu is precomputed per pixel.  92 % of the draws (mu = 0.08) leave at the first test.
-__device__ __forceinline__ int borel(uint32_t r, float mu, float exp_neg_mu) {
-    const float u = u01_open1(r);
-    if (u < exp_neg_mu) return 1;
-    float p = exp_neg_mu, cdf = exp_neg_mu;
-    const float step = mu * exp_neg_mu;
+// Sequential search, used for the tail only.
+__device__ __noinline__ int borel_search(float u, float mu) {
+    const float e = __expf(-mu);
+    float p = e, cdf = e;
+    const float step = mu * e;
     int n = 1;
     while (u >= cdf && n < 256) {
         const float fn = (float)n;
@@ -50,21 +67,18 @@ __device__ __forceinline__ int borel(uint32_t r, float mu, float exp_neg_mu) {
     return n;
 }
 
-// Poisson(lambda).  Small means: sequential inversion.  Large means: Hormann's PTRS transformed
-// rejection (1993), acceptance test in double so that k ~ 1e4 keeps a sharp log-factorial.
-__device__ inline int poisson(BlockReader& rd, float lambda) {
-    if (!(lambda > 0.0f)) return 0;
-    if (lambda < 12.0f) {
-        const float u = u01_open1(rd.next());
-        float p = __expf(-lambda), cdf = p;
-        int k = 0;
-        while (u >= cdf && k < 200) {
-            ++k;
-            p *= lambda / (float)k;
-            cdf += p;
-        }
-        return k;
-    }
+// Borel(mu) with the first four cumulative probabilities precomputed per pixel (cdf.x = P(n<=1) ..
+// cdf.w = P(n<=4)): branch-free for all but P(n>4) of the draws (1e-4 at mu = 0.08).
+__device__ __forceinline__ int borel(uint32_t r, float mu, const float4 cdf) {
+    const float u = u01_open1(r);
+    int n = 1 + (u >= cdf.x) + (u >= cdf.y) + (u >= cdf.z) + (u >= cdf.w);
+    if (u >= cdf.w) n = max(5, borel_search(u, mu));
+    return n;
+}
+
+// Poisson(lambda), large means: Hormann's PTRS transformed rejection (1993), acceptance test in
+// double so that k ~ 1e4 keeps a sharp log-factorial.  Out of line: it is rare and register-hungry.
+__device__ __noinline__ int poisson_ptrs(BlockReader& rd, float lambda) {
     const double lam = (double)lambda;
     const double slam = sqrt(lam), loglam = log(lam);
     const double b = 0.931 + 2.53 * slam;
@@ -84,10 +98,25 @@ __device__ inline int poisson(BlockReader& rd, float lambda) {
     return (int)lam;
 }
 
+// Poisson(lambda).  Small means: sequential inversion.
+__device__ __forceinline__ int poisson(BlockReader& rd, float lambda) {
+    if (!(lambda > 0.0f)) return 0;
+    if (lambda >= 12.0f) return poisson_ptrs(rd, lambda);
+    const float u = u01_open1(rd.next());
+    float p = __expf(-lambda), cdf = p;
+    int k = 0;
+    while (u >= cdf && k < 200) {
+        ++k;
+        p *= lambda / (float)k;
+        cdf += p;
+    }
+    return k;
+}
+
 // Total progeny of n_primary independent Galton-Watson trees with Poisson(mu) offspring, generation
 // by generation: the sum of X Poisson(mu) variables is Poisson(mu X), so a pulse of thousands of pe
 // costs a handful of draws.  Law: generalised Poisson (reference utils/pdf.py:37-42).
-__device__ inline int branching_total(BlockReader& rd, int n_primary, float mu) {
+__device__ __noinline__ int branching_total(BlockReader& rd, int n_primary, float mu) {
     int total = n_primary, gen = n_primary;
     if (!(mu > 0.0f)) return total;
     for (int g = 0; g < 4096 && gen > 0; ++g) {

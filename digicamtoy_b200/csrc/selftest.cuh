@@ -18,8 +18,18 @@ __global__ void k_test_sample(uint32_t kind, float a, float b, uint32_t k0, uint
     float v = 0.0f;
     switch (kind) {
         case SAMPLE_NORMAL: v = normal_one(r.z, r.w); break;
-        case SAMPLE_EXP_GAP: v = exp_gap(r.x, a); break;
-        case SAMPLE_BOREL: v = (float)borel(r.y, a, __expf(-a)); break;
+        case SAMPLE_EXP_GAP: v = exp_gap(r.x, NEG_LN2 * a); break;
+        case SAMPLE_BOREL: {
+            // same four thresholds dct_create computes on the host
+            double pn = exp(-(double)a), cdf = pn;
+            float c[4];
+            for (int n = 1; n <= 4; ++n) {
+                c[n - 1] = (float)fmin(cdf, 1.0);
+                pn *= (double)a * exp(-(double)a) * pow(1.0 + 1.0 / n, n - 1.0);
+                cdf += pn;
+            }
+            v = (float)borel(r.y, a, make_float4(c[0], c[1], c[2], c[3]));
+        } break;
         case SAMPLE_POISSON: { BlockReader rd(key, STREAM_BRANCH, 0); v = (float)poisson(rd, a); } break;
         case SAMPLE_BRANCHING: { BlockReader rd(key, STREAM_BRANCH, 0); v = (float)branching_total(rd, (int)b, a); } break;
         case SAMPLE_UNIFORM: v = u01_open1(r.x); break;

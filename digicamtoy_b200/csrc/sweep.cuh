@@ -7,8 +7,14 @@
 // onset moves to the next cell it retires the oldest bin to shared memory and slides the window.
 // No per-tap address arithmetic, no read-modify-write of shared memory.
 //
-// It consumes the same Philox blocks and performs the same floating-point operations per bin, in
-// the same order, as k_generate_scatter: both kernels produce identical cubes (tests check it).
+// Divergence control (ncu, profiles/r01): the one-cell slide is a predicated select executed by
+// every lane every iteration (22 FSEL) instead of a branchy loop that ran with 7 of 32 lanes; only
+// gaps longer than one cell (0.5 % of pe at 1 GHz) take the loop.  Taps that can only land in
+// dropped or non-existent bins for every lane of the warp are skipped in groups of four using the
+// warp-wide min / max of the cell index (REDUX).
+//
+// It consumes the same Philox blocks and performs the same floating-point operations per kept bin,
+// in the same order, as k_generate_scatter: both kernels produce identical cubes (tests check it).
 //
 // Replaces the dense (pixel, pe, bin) spline evaluation of compute_analog_signal
 // (reference digicamtoy/tracegenerator/__init__.py:350-362).
@@ -21,6 +27,7 @@ constexpr int SWEEP_TAPS = 22;            // 88 ns template / 4 ns sampling
 constexpr int SWEEP_PHASES = 8;           // 4 ns sampling / 0.5 ns knots
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_MAX_BINS = 256;
+constexpr int SWEEP_GROUP = 4;            // taps per skip group
 constexpr double SWEEP_MIN_MEAN_PE = 24.0;   // below this the scatter kernel wins (few pe per trace)
 
 inline bool sweep_supported(const DevParams& p) {
@@ -30,31 +37,27 @@ inline bool sweep_supported(const DevParams& p) {
 }
 
 template <int TAPS, int PHASES, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 5)
 k_generate_sweep(const GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& p = a.p;
     const int tid = threadIdx.x;
     const int B = p.B;
 
-    float* Vall = reinterpret_cast<float*>(smem_raw);
-    float4* tab_s = reinterpret_cast<float4*>(smem_raw + (size_t)B * NT * sizeof(float));
-    int16_t* out_s = reinterpret_cast<int16_t*>(tab_s + TAPS * PHASES);
+    float4* tab_s = reinterpret_cast<float4*>(smem_raw);
+    float* rows = reinterpret_cast<float*>(tab_s + TAPS * PHASES);
     for (int i = tid; i < TAPS * PHASES; i += NT) tab_s[i] = p.poly[i];
-    float* V = Vall + tid;
-    for (int b = 0; b < B; ++b) V[b * NT] = 0.0f;
+    float* row = rows + tid * row_stride(B);
+    for (int b = 0; b < B; ++b) row[b] = 0.0f;
     __syncthreads();
 
     const uint64_t trace0 = (uint64_t)blockIdx.x * NT;
     if (trace0 + tid < a.n_traces) {
         const TraceId t = trace_id(a, trace0 + tid);
         const float rate = p.rate[t.pixel];
-        const float xt = p.xt[t.pixel];
-        const float exp_neg_xt = p.exp_neg_xt[t.pixel];
-        const float sigma1 = p.sigma1[t.pixel];
+        const PixelNsb q = load_pixel_nsb(p, t.pixel);
 
         if (rate > 0.0f) {
-            const float inv_rate = p.inv_rate[t.pixel];
             float W[TAPS];                                   // W[j] <-> simulated bin cell+1+j
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) W[j] = 0.0f;
@@ -62,49 +65,67 @@ k_generate_sweep(const GenArgs a) {
             int cell = p.cell0;
             float off = p.off0;
             const int kb_shift = 1 - p.n_drop;               // kept index of W[0] = cell + kb_shift
+            const int first_needed = p.n_drop - 1;           // tap j is kept iff j >= first_needed - cell
+            const int last_needed = p.n_drop + B - 1;        //             and j <  last_needed  - cell
             for (uint32_t i = 0;; ++i) {
                 const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                const float gap = exp_gap(r.x, inv_rate);
+                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
                 elapsed += gap;
                 if (elapsed >= p.span) break;
-                const int cell_before = cell;
+                int kb = cell + kb_shift;
                 int k = advance_onset(p, gap, cell, off);
-                if (k >= TAPS) {
-                    // long gap: the whole window retires at once
+                // slide by one cell: predicated, all lanes
+                const bool one = k >= 1;
+                if (one && (unsigned)kb < (unsigned)B) row[kb] = W[0];
 #pragma unroll
-                    for (int j = 0; j < TAPS; ++j) {
-                        const int kb = cell_before + kb_shift + j;
-                        if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[j];
-                        W[j] = 0.0f;
-                    }
-                } else {
-                    int kb = cell_before + kb_shift;
-                    for (; k > 0; --k, ++kb) {
-                        if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[0];
+                for (int j = 0; j < TAPS - 1; ++j) W[j] = one ? W[j + 1] : W[j];
+                W[TAPS - 1] = one ? 0.0f : W[TAPS - 1];
+                if (k >= 2) {                                 // rare: gap longer than a cell
+                    ++kb;
+                    if (k > TAPS) {
 #pragma unroll
-                        for (int j = 0; j < TAPS - 1; ++j) W[j] = W[j + 1];
-                        W[TAPS - 1] = 0.0f;
+                        for (int j = 0; j < TAPS; ++j) {
+                            if ((unsigned)(kb + j) < (unsigned)B) row[kb + j] = W[j];
+                            W[j] = 0.0f;
+                        }
+                    } else {
+                        for (--k; k > 0; --k, ++kb) {
+                            if ((unsigned)kb < (unsigned)B) row[kb] = W[0];
+#pragma unroll
+                            for (int j = 0; j < TAPS - 1; ++j) W[j] = W[j + 1];
+                            W[TAPS - 1] = 0.0f;
+                        }
                     }
                 }
-                const float A = nsb_amplitude(r, xt, exp_neg_xt, sigma1);
+                const float A = nsb_amplitude(r, q);
                 int f; float u;
                 phase_of(p, p.dt - off, f, u);
-                const float4* row = tab_s + f;
+                const float4* trow = tab_s + f;
+                // warp-uniform tap range: skip groups no lane needs
+                const unsigned act = __activemask();
+                const int j_lo = first_needed - __reduce_max_sync(act, cell);
+                const int j_hi = last_needed - __reduce_min_sync(act, cell);
 #pragma unroll
-                for (int j = 0; j < TAPS; ++j) W[j] = __fmaf_rn(A, horner(row[j * PHASES], u), W[j]);
+                for (int g0 = 0; g0 < TAPS; g0 += SWEEP_GROUP) {
+                    if (g0 + SWEEP_GROUP > j_lo && g0 < j_hi) {
+#pragma unroll
+                        for (int j = g0; j < g0 + SWEEP_GROUP && j < TAPS; ++j)
+                            W[j] = __fmaf_rn(A, horner(trow[j * PHASES], u), W[j]);
+                    }
+                }
             }
             // retire what is left in the window
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
                 const int kb = cell + kb_shift + j;
-                if ((unsigned)kb < (unsigned)B) V[kb * NT] = W[j];
+                if ((unsigned)kb < (unsigned)B) row[kb] = W[j];
             }
         }
-        add_signal_pulses<NT>(a, t, p.coef32, V, xt, sigma1);
-        digitise_trace<NT>(p, t, V, out_s + tid * B);
+        add_signal_pulses(a, t, p.coef32, row, q.xt, q.sigma1);
+        digitise_trace(p, t, row);
     }
     __syncthreads();
-    store_run<NT>(a, trace0, out_s);
+    store_run<NT>(a, trace0, rows);
 }
 
 inline int launch_sweep(int device, int /*sm_count*/, const GenArgs& a, cudaStream_t st, char* err, size_t err_len) {

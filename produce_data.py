@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's ``produce_data.py`` (reference produce_data.py:16-147).
+
+Same command line (``-y/--yaml_config``, ``-d/--debug``), same YAML schema (generator keyword
+arguments + ``output_directory``, ``file_basename``, ``events_per_level``), same refusal to
+overwrite, same NSB-major file numbering, same datasets:
+
+    config/<every option>, config/date
+    data/true_baseline (P,), data/adc_count uint16 (E,P,B), data/time (E,P,K), data/charge (E,P,K)
+
+but every level is generated on the GPU in one chunked call (``NTraceGenerator.generate_host``,
+D2H overlapped with generation) instead of an event-by-event Python loop.  Output is HDF5 when
+h5py is importable; otherwise the identical logical layout goes into ``<file>.npz`` (keys are the
+dataset paths).  Launched under torchrun, the (nsb, n_photon) levels are dealt round-robin to the
+ranks -- the replacement for the reference's SLURM job array (jobs.sh, run.sh).
+
+Additions (all optional): ``--seed``, ``--output_directory``, ``--events_per_level``, ``--device``.
+"""
+import copy
+import datetime
+import logging
+import os
+import sys
+from optparse import OptionParser
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def natural_size(n):
+    for unit in ('Bytes', 'KiB', 'MiB', 'GiB', 'TiB'):
+        if n < 1024 or unit == 'TiB':
+            return ('%d %s' % (n, unit)) if unit == 'Bytes' else ('%.1f %s' % (n, unit))
+        n /= 1024.0
+
+
+def load_options(argv=None):
+    parser = OptionParser()
+    parser.add_option('-y', '--yaml_config', dest='yaml_config',
+                      help='full path of the yaml configuration function', default='options/ac_dc_scan.yaml')
+    parser.add_option('-d', '--debug', action='store_true', dest='debug', default=False, help='move to debug')
+    parser.add_option('--seed', dest='cli_seed', type='int', default=None, help='base seed (level i uses seed+i)')
+    parser.add_option('--output_directory', dest='cli_output_directory', default=None)
+    parser.add_option('--events_per_level', dest='cli_events_per_level', type='int', default=None)
+    parser.add_option('--device', dest='cli_device', type='int', default=None)
+    options, _ = parser.parse_args(argv)
+    import yaml
+    loader = getattr(yaml, 'CSafeLoader', yaml.SafeLoader)
+    with open(options.yaml_config) as stream:
+        for key, val in yaml.load(stream, Loader=loader).items():
+            options.__dict__[key] = val                                   # produce_data.py:39-45
+    cli = {k: options.__dict__.pop(k) for k in list(options.__dict__) if k.startswith('cli_')}
+    if cli['cli_output_directory'] is not None:
+        options.output_directory = cli['cli_output_directory']
+    if cli['cli_events_per_level'] is not None:
+        options.events_per_level = cli['cli_events_per_level']
+    return options, cli
+
+
+def level_filenames(options):
+    n = len(options.n_photon) * len(options.nsb_rate)
+    return [os.path.join(options.output_directory, options.file_basename.format(i)) for i in range(n)]
+
+
+class Writer:
+    """HDF5 through h5py when present, else an .npz bundle with the dataset paths as keys."""
+
+    def __init__(self, filename):
+        try:
+            import h5py
+            self.h5 = h5py.File(filename, 'w')
+            self.path = filename
+            self.store = None
+        except ImportError:
+            self.h5 = None
+            self.path = filename + '.npz'
+            self.store = {}
+
+    def put(self, path, data, compress=False, dtype=None):
+        if self.h5 is not None:
+            group, name = path.split('/')
+            g = self.h5.require_group(group)
+            kw = dict(chunks=True, compression='gzip') if compress and np.ndim(data) > 0 else {}
+            if dtype is not None:
+                kw['dtype'] = dtype
+            g.create_dataset(name, data=data, **kw)
+        else:
+            arr = np.asarray(data) if dtype is None else np.asarray(data, dtype=dtype)
+            if arr.dtype == object:
+                arr = np.asarray(str(data))
+            self.store[path] = arr
+
+    def close(self):
+        if self.h5 is not None:
+            self.h5.close()
+        else:
+            np.savez_compressed(self.path[:-4], **self.store)
+        return self.path
+
+
+def main(argv=None):
+    log = logging
+    options, cli = load_options(argv)
+    log.getLogger().setLevel(logging.DEBUG if options.debug else logging.INFO)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    device = cli['cli_device'] if cli['cli_device'] is not None else int(os.environ.get('LOCAL_RANK', '0'))
+
+    for filename in level_filenames(options):                             # produce_data.py:47-57
+        if os.path.exists(filename) or os.path.exists(filename + '.npz'):
+            log.error('File {} already exists'.format(filename))
+            return 1
+
+    log.debug(vars(options))
+    log.info('\t\t-|> Create the Monte Carlo data set')
+
+    from digicamtoy_b200 import NTraceGenerator
+    options_generator = copy.copy(options)
+    events_per_level = options_generator.events_per_level
+    base_seed = cli['cli_seed']
+    file_number = 0
+    written = []
+    for nsb_rate in options.nsb_rate:                                     # NSB-major numbering (:71-93)
+        options_generator.nsb_rate = nsb_rate
+        for n_photon in options.n_photon:
+            options_generator.n_photon = n_photon
+            my_turn = (file_number % world) == rank
+            filename = os.path.join(options.output_directory, options.file_basename.format(file_number))
+            if my_turn:
+                kwargs = dict(vars(options_generator))
+                kwargs.pop('seed', None)
+                seed = None if base_seed is None else base_seed + file_number
+                generator = NTraceGenerator(seed=seed, device=device, **kwargs)
+                writer = Writer(filename)
+                for key, val in vars(options_generator).items():          # config group (:95-100)
+                    writer.put('config/' + key, val)
+                writer.put('config/seed', np.uint64(generator.seed))
+                writer.put('data/true_baseline', generator.true_baseline, compress=True)
+                adc_count, cherenkov_time, cherenkov_photon = generator.generate_host(
+                    events_per_level, first_event=0)                      # replaces the loop :119-126
+                log.info('\t\t-|> Saving data to {}'.format(writer.path))
+                writer.put('data/adc_count', adc_count, compress=True, dtype=np.uint16)
+                writer.put('data/time', cherenkov_time.astype(np.float64), compress=True)
+                writer.put('data/charge', cherenkov_photon.astype(np.float64), compress=True)
+                writer.put('config/date', str(datetime.datetime.now()))
+                path = writer.close()
+                generator.close()
+                log.info('\t\t-|> File saved! Size = {}'.format(natural_size(os.path.getsize(path))))
+                written.append(path)
+            file_number += 1
+    return written
+
+
+if __name__ == '__main__':
+    out = main()
+    sys.exit(out if isinstance(out, int) else 0)

@@ -270,11 +270,11 @@ def test_degenerate_configs():
     c = cube(g, 5)
     assert np.array_equal(c[:, 0], np.full((5, 50), 10)) and np.all(c[:, 1] == 20) and np.all(c[:, 2] == 31)
     # deterministic pulse: poisson off, no crosstalk, no smearing -> analytic trace, incl. t on a sample
-    g = gen(n_pixels=2, nsb_rate=0, crosstalk=0, sigma_e=0, sigma_1=0, n_photon=50, poisson=False,
+    g = gen(n_pixels=2, nsb_rate=0, crosstalk=0, sigma_e=0, sigma_1=0, n_photon=500, poisson=False,
             gain_nsb=False, gain=5.0, baseline=100, time_signal=20, jitter=0)
     c = cube(g, 3)
     t = np.arange(0, 200, 4)
-    want = np.round(100 + 5.0 * 50 * g.get_pulse_shape(t, t_0=20)).astype(int)
+    want = np.round(100 + 5.0 * 500 * g.get_pulse_shape(t, t_0=20)).astype(int)
     assert np.abs(c[0, 0] - want).max() <= 1 and (c[0, 0] != want).sum() <= 1
     assert want[5] > 100                                          # h(0) > 0 counted at t == time_signal
     # zero events / one pixel / odd bin count
@@ -347,7 +347,7 @@ def test_stats_kernel_matches_numpy():
 def test_write_calibrate_kernel():
     import torch
     from digicamtoy_b200 import native
-    buf = torch.full((1 << 20) + 3, -1, dtype=torch.int16, device='cuda')
+    buf = torch.full(((1 << 20) + 3,), -1, dtype=torch.int16, device='cuda')
     native.write_calibrate(buf.data_ptr(), buf.numel())
     torch.cuda.synchronize()
     assert int((buf < 0).sum()) == 0
