@@ -59,6 +59,8 @@ struct dct_handle {
     int n_table_entries = 0;
     size_t gen_smem = 0;
     double mean_pe_per_trace = 0.0;
+    double mean_true_baseline = 0.0;   // baseline + NSB shift, averaged over pixels (stats window)
+    double mean_baseline = 0.0;
     // host-output pipeline (dct_generate_host), created lazily
     cudaStream_t s_gen = nullptr, s_copy = nullptr;
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -237,6 +239,20 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         pe_sum += c->nsb_rate[i] * (c->t_end - c->t0);
     }
     h->mean_pe_per_trace = pe_sum / P;
+    {   // expected pedestal incl. the NSB shift: baseline + gain rate tau / (1 - xt), tau = integral of h
+        double tau = 0.0;
+        for (int m = 0; m < n_iv; ++m) {
+            const double* k = c->coef + 4 * m;
+            tau += ((k[3] * dx / 4 + k[2] / 3) * dx + k[1] / 2) * dx * dx + k[0] * dx;
+        }
+        double acc = 0.0;
+        for (int i = 0; i < P; ++i)
+            acc += c->baseline[i] + c->gain[i] * c->nsb_rate[i] * tau / (1.0 - c->crosstalk[i]);
+        h->mean_true_baseline = acc / P;
+        double bsum = 0.0;
+        for (int i = 0; i < P; ++i) bsum += std::nearbyint(c->baseline[i]);
+        h->mean_baseline = bsum / P;
+    }
     for (size_t i = 0; i < (size_t)P * K; ++i) {
         f_npe[i] = (float)c->n_photon[i];
         f_tsig[i] = (float)c->time_signal[i];
@@ -503,6 +519,30 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
     if (adc_hist && n_hist > 16384) return fail(DCT_E_UNSUPPORTED, "ADC histogram wider than 16384 bins");
     if (charge_hist && (a.B > 32 * dct::STATS_BINS_PER_LANE || n_charge_bins == 0))
         return fail(DCT_E_UNSUPPORTED, "charge histogram needs <= 128 bins per trace and n_charge_bins > 0");
+    // the fast kernel derives the power sums from the histogram, so it needs the histogram buffer
+    const bool fast = (a.B % 2 == 0) && a.B <= 128 && (reinterpret_cast<uintptr_t>(adc) & 3) == 0 &&
+                      (adc_hist != nullptr || moments == nullptr) && n_hist <= 16384;
+    if (fast) {
+        // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
+        // the charge of a trace that holds nothing but that pedestal shift
+        const int win_lo = (int)std::floor(h->mean_true_baseline) - dct::STATS_WIN / 2 + 4;
+        const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
+        int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
+        charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));
+        const size_t smem = ((size_t)n_hist + dct::STATS_CHARGE_WIN +
+                             (size_t)dct::STATS_FAST_WARPS * dct::STATS_WIN * 16) * sizeof(unsigned int);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(dct::k_stats_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint64_t blocks = (uint64_t)h->sm_count * 3;
+        const uint64_t n_warps = blocks * dct::STATS_FAST_WARPS;
+        // (pixel, event-slice) work items: ~4 per warp for balance, never more slices than events
+        uint64_t n_slices = (4 * n_warps + a.P - 1) / a.P;
+        n_slices = std::max<uint64_t>(1, std::min<uint64_t>(n_slices, n_events));
+        dct::k_stats_fast<<<(unsigned)blocks, dct::STATS_FAST_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            a, win_lo, (int)n_slices, charge_win_lo);
+        CK(cudaGetLastError());
+        return DCT_OK;
+    }
     const size_t smem = adc_hist ? (size_t)n_hist * sizeof(unsigned int) : 0;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(dct::k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -108,6 +108,197 @@ k_stats(const StatsArgs a) {
     }
 }
 
+// Fast path (even B <= 128, 4-byte aligned cube).  ncu/CUDA-event history (profiles/r01): the first
+// K3 spent longer than K1 on the dark run -- plain shared-memory atomics serialise when every sample
+// sits within a few LSB of the pedestal, and float64 power sums cost ~25 instructions per sample.
+// This version
+//   * reads 32-bit words (two samples per lane per load), four traces in flight per warp;
+//   * gives every lane a private column hist[value - win_lo][lane] of 16-bit counters for the
+//     STATS_WIN values around the pedestal: no atomics, no races; samples outside the window use
+//     the CTA-wide atomic histogram;
+//   * keeps per-bin sums in 64-bit integers (one IMAD.WIDE each) and derives the raw power sums
+//     sum x^k from the CTA histogram when it is flushed, not per sample.
+constexpr int STATS_WIN = 64;
+constexpr int STATS_FAST_WARPS = 8;
+constexpr int STATS_FLUSH_TRACES = 8192;      // 4 samples per lane per trace: 16-bit counters stay < 2^15
+
+struct StatsLane {
+    long long bs[4], bq[4];
+};
+
+__device__ __forceinline__ void stats_word(const StatsArgs& a, uint32_t word, int slot, unsigned short* priv,
+                                           unsigned int* hist_s, int win_lo, StatsLane& L, int& ts,
+                                           long long& tq) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int v = (int)(int16_t)(h ? (word >> 16) : (word & 0xffffu));
+        L.bs[slot + h] += v;
+        L.bq[slot + h] += (long long)v * v;
+        ts += v;
+        tq += (long long)v * v;
+        if (a.adc_hist) {
+            const unsigned w = (unsigned)(v - win_lo);
+            if (w < (unsigned)STATS_WIN) priv[w * 32] += 1;
+            else atomicAdd(&hist_s[v - a.adc_min], 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void stats_fold_private(unsigned short* priv_all, unsigned int* hist_s, int win_lo,
+                                                   int adc_min, int n_hist) {
+    // all warps of the CTA: fold every lane-private column into the CTA histogram and clear it
+    for (int i = threadIdx.x; i < STATS_FAST_WARPS * STATS_WIN; i += blockDim.x) {
+        unsigned short* col = priv_all + (size_t)i * 32;
+        unsigned int c = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int k = (l + threadIdx.x) & 31;
+            c += col[k];
+            col[k] = 0;
+        }
+        const int v = win_lo + (i % STATS_WIN) - adc_min;
+        if (c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+    }
+}
+
+constexpr int STATS_T = 8;                    // traces per pipeline stage
+constexpr int STATS_CHARGE_WIN = 1024;       // CTA-private window of the charge histogram
+
+// Work item = (pixel, slice of events): a warp walks the traces of ONE pixel, so the per-pixel sums
+// stay in registers and are flushed with two atomics per item (the first version issued three
+// global atomics per trace onto a few hundred hot addresses and was bound by L2 atomic
+// serialisation: 8-11 ms per 2 GB cube instead of ~1 ms).
+__global__ void __launch_bounds__(STATS_FAST_WARPS * 32, 3)
+k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
+    extern __shared__ unsigned int smem_u[];
+    const int n_hist = a.adc_max - a.adc_min + 1;
+    unsigned int* hist_s = smem_u;                                               // [n_hist]
+    unsigned int* charge_s = smem_u + n_hist;                                    // [STATS_CHARGE_WIN]
+    unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;
+    for (int i = threadIdx.x; i < n_hist + STATS_CHARGE_WIN + STATS_FAST_WARPS * STATS_WIN * 16; i += blockDim.x)
+        smem_u[i] = 0u;
+    __syncthreads();
+
+    const uint64_t warp = (uint64_t)blockIdx.x * STATS_FAST_WARPS + wib;
+    const uint64_t n_warps = (uint64_t)gridDim.x * STATS_FAST_WARPS;
+    const int wpr = a.B >> 1;                                                    // 32-bit words per trace
+    const bool has0 = lane < wpr, has1 = lane + 32 < wpr;
+    StatsLane L;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { L.bs[r] = 0; L.bq[r] = 0; }
+    const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
+    const uint64_t n_events = a.n_traces / (uint64_t)a.P;
+    const uint64_t n_items = (uint64_t)a.P * n_slices;
+    const uint64_t row_words = (uint64_t)a.P * wpr;                              // words between events
+    int lane_samples = 0;                                                        // bound on a private counter
+
+    for (uint64_t item = warp; item < n_items; item += n_warps) {
+        const int pixel = (int)(item % (uint64_t)a.P);
+        const uint64_t slice = item / (uint64_t)a.P;
+        const uint64_t e_begin = slice * n_events / n_slices, e_end = (slice + 1) * n_events / n_slices;
+        const long long charge_ref = (long long)a.B * llrintf(a.baseline[pixel]);
+        double pix_s = 0.0, pix_q = 0.0;
+        const uint32_t* base = cube + (uint64_t)pixel * wpr;
+        // software pipeline: the words of the next STATS_T traces are in flight while the current
+        // ones are processed (the first version was latency-bound: ~13 KB in flight per SM)
+        uint32_t w0[STATS_T], w1[STATS_T], n0[STATS_T], n1[STATS_T];
+#pragma unroll
+        for (int tr = 0; tr < STATS_T; ++tr) {
+            const bool ok = e_begin + tr < e_end;
+            const uint32_t* row = base + (e_begin + tr) * row_words;
+            w0[tr] = (ok && has0) ? __ldcs(row + lane) : 0u;
+            w1[tr] = (ok && has1) ? __ldcs(row + lane + 32) : 0u;
+        }
+        for (uint64_t e = e_begin; e < e_end; e += STATS_T) {
+#pragma unroll
+            for (int tr = 0; tr < STATS_T; ++tr) {
+                const bool ok = e + STATS_T + tr < e_end;
+                const uint32_t* row = base + (e + STATS_T + tr) * row_words;
+                n0[tr] = (ok && has0) ? __ldcs(row + lane) : 0u;
+                n1[tr] = (ok && has1) ? __ldcs(row + lane + 32) : 0u;
+            }
+#pragma unroll
+            for (int tr = 0; tr < STATS_T; ++tr) {
+                if (e + tr >= e_end) continue;
+                int ts = 0;
+                long long tq = 0;
+                if (has0) stats_word(a, w0[tr], 0, priv, hist_s, win_lo, L, ts, tq);
+                if (has1) stats_word(a, w1[tr], 2, priv, hist_s, win_lo, L, ts, tq);
+                if (a.pixel_sum || a.charge_hist) {
+                    ts = __reduce_add_sync(0xffffffffu, ts);
+                    pix_s += (double)ts;
+                    if (a.pixel_sumsq) pix_q += (double)tq;                      // reduced once per item
+                    if (a.charge_hist && lane == 0) {
+                        long long bin = (long long)ts - charge_ref - a.charge_lo;
+                        bin = bin < 0 ? 0 : (bin >= a.n_charge_bins ? a.n_charge_bins - 1 : bin);
+                        const long long w = bin - charge_win_lo;
+                        if (w >= 0 && w < STATS_CHARGE_WIN) atomicAdd(&charge_s[w], 1u);
+                        else atomicAdd(a.charge_hist + bin, 1ull);
+                    }
+                }
+            }
+#pragma unroll
+            for (int tr = 0; tr < STATS_T; ++tr) { w0[tr] = n0[tr]; w1[tr] = n1[tr]; }
+            lane_samples += 4 * STATS_T;
+            if (a.adc_hist && lane_samples >= 60000) {                           // warp-private: fold my columns
+                __syncwarp();
+                for (int w = 0; w < STATS_WIN; ++w) {
+                    const unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)priv[w * 32]);
+                    priv[w * 32] = 0;
+                    const int v = win_lo + w - a.adc_min;
+                    if (lane == 0 && c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+                }
+                lane_samples = 0;
+            }
+        }
+        if (a.pixel_sum) {
+            pix_q = warp_sum(pix_q);
+            if (lane == 0) {
+                atomicAdd(a.pixel_sum + pixel, pix_s);
+                if (a.pixel_sumsq) atomicAdd(a.pixel_sumsq + pixel, pix_q);
+            }
+        }
+    }
+    // lane owns bins 2*lane, 2*lane+1 (first word) and 2*(lane+32), 2*(lane+32)+1 (second word)
+    const int bins[4] = {2 * lane, 2 * lane + 1, 2 * (lane + 32), 2 * (lane + 32) + 1};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (bins[r] < a.B) {
+            if (a.bin_sum) atomicAdd(a.bin_sum + bins[r], (double)L.bs[r]);
+            if (a.bin_sumsq) atomicAdd(a.bin_sumsq + bins[r], (double)L.bq[r]);
+        }
+    __syncthreads();
+    if (a.adc_hist) {
+        stats_fold_private(priv_all, hist_s, win_lo, a.adc_min, n_hist);
+        __syncthreads();
+    }
+    if (a.charge_hist)
+        for (int i = threadIdx.x; i < STATS_CHARGE_WIN; i += blockDim.x) {
+            const unsigned int c = charge_s[i];
+            if (c && charge_win_lo + i < a.n_charge_bins) atomicAdd(a.charge_hist + charge_win_lo + i, (unsigned long long)c);
+        }
+    // flush the CTA histogram; the raw power sums come from it (exact: integers < 2^53 per CTA)
+    double m[4] = {0, 0, 0, 0};
+    if (a.adc_hist) {
+        for (int i = threadIdx.x; i < n_hist; i += blockDim.x) {
+            const unsigned int c = hist_s[i];
+            if (c) {
+                atomicAdd(a.adc_hist + i, (unsigned long long)c);
+                const double x = (double)(i + a.adc_min), cd = (double)c;
+                m[0] += cd * x; m[1] += cd * x * x; m[2] += cd * x * x * x; m[3] += cd * x * x * x * x;
+            }
+        }
+    }
+    if (a.moments && a.adc_hist) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = warp_sum(m[k]);
+            if (lane == 0 && v != 0.0) atomicAdd(a.moments + k, v);
+        }
+    }
+}
+
 // K0: nothing but the stores K1 issues.  16 bytes per thread per iteration, grid-stride.
 __global__ void __launch_bounds__(256)
 k_write_calibrate(int4* __restrict__ dst, size_t n_vec, int16_t* __restrict__ tail, size_t n_tail) {

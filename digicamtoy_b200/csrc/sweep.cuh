@@ -36,8 +36,29 @@ inline bool sweep_supported(const DevParams& p) {
            gen_smem_bytes(p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS) <= 227 * 1024;
 }
 
+// W[j] <- W[j+1] (j < TAPS-1), W[TAPS-1] <- 0 for the lanes with `go`; a no-op for the others.
+// Written as predicated moves on read-write operands so that every W[j] keeps its register:
+// the C++ forms (select or branch) made ptxas keep two copies of the window and move all 22
+// values back at the end of every iteration (profiles/r01: 22-44 extra MOV/FSEL per pe).
+template <int TAPS>
+__device__ __forceinline__ void slide_window(float (&W)[TAPS], bool go) {
+    static_assert(TAPS == 22, "slide_window is written out for 22 taps");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %22, 0;\n\t"
+        "@p mov.f32 %0, %1;\n\t@p mov.f32 %1, %2;\n\t@p mov.f32 %2, %3;\n\t@p mov.f32 %3, %4;\n\t"
+        "@p mov.f32 %4, %5;\n\t@p mov.f32 %5, %6;\n\t@p mov.f32 %6, %7;\n\t@p mov.f32 %7, %8;\n\t"
+        "@p mov.f32 %8, %9;\n\t@p mov.f32 %9, %10;\n\t@p mov.f32 %10, %11;\n\t@p mov.f32 %11, %12;\n\t"
+        "@p mov.f32 %12, %13;\n\t@p mov.f32 %13, %14;\n\t@p mov.f32 %14, %15;\n\t@p mov.f32 %15, %16;\n\t"
+        "@p mov.f32 %16, %17;\n\t@p mov.f32 %17, %18;\n\t@p mov.f32 %18, %19;\n\t@p mov.f32 %19, %20;\n\t"
+        "@p mov.f32 %20, %21;\n\t@p mov.f32 %21, 0f00000000;\n\t}"
+        : "+f"(W[0]), "+f"(W[1]), "+f"(W[2]), "+f"(W[3]), "+f"(W[4]), "+f"(W[5]), "+f"(W[6]), "+f"(W[7]),
+          "+f"(W[8]), "+f"(W[9]), "+f"(W[10]), "+f"(W[11]), "+f"(W[12]), "+f"(W[13]), "+f"(W[14]),
+          "+f"(W[15]), "+f"(W[16]), "+f"(W[17]), "+f"(W[18]), "+f"(W[19]), "+f"(W[20]), "+f"(W[21])
+        : "r"((int)go));
+}
+
 template <int TAPS, int PHASES, int NT>
-__global__ void __launch_bounds__(NT, 5)
+__global__ void __launch_bounds__(NT, 6)
 k_generate_sweep(const GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& p = a.p;
@@ -77,9 +98,7 @@ k_generate_sweep(const GenArgs a) {
                 // slide by one cell: predicated, all lanes
                 const bool one = k >= 1;
                 if (one && (unsigned)kb < (unsigned)B) row[kb] = W[0];
-#pragma unroll
-                for (int j = 0; j < TAPS - 1; ++j) W[j] = one ? W[j + 1] : W[j];
-                W[TAPS - 1] = one ? 0.0f : W[TAPS - 1];
+                slide_window<TAPS>(W, one);
                 if (k >= 2) {                                 // rare: gap longer than a cell
                     ++kb;
                     if (k > TAPS) {
