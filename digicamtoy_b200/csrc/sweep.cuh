@@ -36,13 +36,26 @@ inline bool sweep_supported(const DevParams& p) {
            gen_smem_bytes(p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS) <= 227 * 1024;
 }
 
+// Packed FP32 FMA (Blackwell FFMA2): two IEEE fma.rn.f32 in one issue slot.  Bit-identical to two
+// scalar __fmaf_rn, so the scatter kernel (scalar) and this kernel still agree exactly.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 // W[j] <- W[j+1] (j < TAPS-1), W[TAPS-1] <- 0 for the lanes with `go`; a no-op for the others.
 // Written as predicated moves on read-write operands so that every W[j] keeps its register:
 // the C++ forms (select or branch) made ptxas keep two copies of the window and move all 22
 // values back at the end of every iteration (profiles/r01: 22-44 extra MOV/FSEL per pe).
 template <int TAPS>
 __device__ __forceinline__ void slide_window(float (&W)[TAPS], bool go) {
-    static_assert(TAPS == 22, "slide_window is written out for 22 taps");
+    static_assert(TAPS == 22 && TAPS % 2 == 0, "slide_window is written out for 22 taps");
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %22, 0;\n\t"
         "@p mov.f32 %0, %1;\n\t@p mov.f32 %1, %2;\n\t@p mov.f32 %2, %3;\n\t@p mov.f32 %3, %4;\n\t"
@@ -67,7 +80,15 @@ k_generate_sweep(const GenArgs a) {
 
     float4* tab_s = reinterpret_cast<float4*>(smem_raw);
     float* rows = reinterpret_cast<float*>(tab_s + TAPS * PHASES);
-    for (int i = tid; i < TAPS * PHASES; i += NT) tab_s[i] = p.poly[i];
+    // pair-interleaved copy of the polyphase table for FFMA2: for tap pair m = (2m, 2m+1), phase f
+    //   lo[m*PHASES + f] = (c0_a, c0_b, c1_a, c1_b)      hi[m*PHASES + f] = (c2_a, c2_b, c3_a, c3_b)
+    float4* tab_hi = tab_s + (TAPS / 2) * PHASES;
+    for (int i = tid; i < (TAPS / 2) * PHASES; i += NT) {
+        const int m = i / PHASES, f = i - m * PHASES;
+        const float4 ca = p.poly[(2 * m) * PHASES + f], cb = p.poly[(2 * m + 1) * PHASES + f];
+        tab_s[i] = make_float4(ca.x, cb.x, ca.y, cb.y);
+        tab_hi[i] = make_float4(ca.z, cb.z, ca.w, cb.w);
+    }
     float* row = rows + tid * row_stride(B);
     for (int b = 0; b < B; ++b) row[b] = 0.0f;
     __syncthreads();
@@ -119,7 +140,9 @@ k_generate_sweep(const GenArgs a) {
                 const float A = nsb_amplitude(r, q);
                 int f; float u;
                 phase_of(p, p.dt - off, f, u);
-                const float4* trow = tab_s + f;
+                const float4* tlo = tab_s + f;
+                const float4* thi = tab_hi + f;
+                const float2 uu = make_float2(u, u), AA = make_float2(A, A);
                 // warp-uniform tap range: skip groups no lane needs
                 const unsigned act = __activemask();
                 const int j_lo = first_needed - __reduce_max_sync(act, cell);
@@ -128,8 +151,15 @@ k_generate_sweep(const GenArgs a) {
                 for (int g0 = 0; g0 < TAPS; g0 += SWEEP_GROUP) {
                     if (g0 + SWEEP_GROUP > j_lo && g0 < j_hi) {
 #pragma unroll
-                        for (int j = g0; j < g0 + SWEEP_GROUP && j < TAPS; ++j)
-                            W[j] = __fmaf_rn(A, horner(trow[j * PHASES], u), W[j]);
+                        for (int j = g0; j < g0 + SWEEP_GROUP && j < TAPS; j += 2) {
+                            const float4 lo = tlo[(j / 2) * PHASES], hi = thi[(j / 2) * PHASES];
+                            float2 t = ffma2(make_float2(hi.z, hi.w), uu, make_float2(hi.x, hi.y));
+                            t = ffma2(t, uu, make_float2(lo.z, lo.w));
+                            t = ffma2(t, uu, make_float2(lo.x, lo.y));
+                            const float2 w = ffma2(AA, t, make_float2(W[j], W[j + 1]));
+                            W[j] = w.x;
+                            W[j + 1] = w.y;
+                        }
                     }
                 }
             }
