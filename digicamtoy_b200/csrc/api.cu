@@ -521,7 +521,8 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         return fail(DCT_E_UNSUPPORTED, "charge histogram needs <= 128 bins per trace and n_charge_bins > 0");
     // the fast kernel derives the power sums from the histogram, so it needs the histogram buffer
     const bool fast = (a.B % 2 == 0) && a.B <= 128 && (reinterpret_cast<uintptr_t>(adc) & 3) == 0 &&
-                      (adc_hist != nullptr || moments == nullptr) && n_hist <= 16384;
+                      (adc_hist != nullptr || moments == nullptr) && n_hist <= 16384 &&
+                      std::max(std::abs(a.adc_min), std::abs(a.adc_max)) <= 11585;
     if (fast) {
         // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
         // the charge of a trace that holds nothing but that pedestal shift

@@ -46,12 +46,14 @@ __device__ __forceinline__ float template_at(const DevParams& p, const float4* c
     return horner(coef[m], u);
 }
 
-// Digitise one sample: analog sum -> LSB.  Same operation order as the reference (x gain :362,
-// + noise :371, + baseline :379, round half-to-even :380), then saturate.  The rounding is the
-// float add of 1.5*2^23 (round-to-nearest-even in hardware, FMA pipe) instead of an F2I (XU pipe).
-__device__ __forceinline__ int digitise(float acc, float gain, float noise, float baseline,
+// Digitise one sample: analog sum -> LSB:  clamp(rint_half_even(acc*gain + noise + baseline)).
+// (The reference adds in the order :362, :371, :379 in float64; here two FFMA in float32 -- the
+// stochastic kernels only have to agree with each other bit for bit, which they do because both
+// call this function; the replay kernels keep the reference's operation order.)
+// Rounding = float add of 1.5*2^23 (round-to-nearest-even in hardware, FMA pipe), no F2I (XU pipe).
+__device__ __forceinline__ int digitise(float acc, float gain, float z, float sigma_e, float baseline,
                                         float lo, float hi) {
-    float v = __fadd_rn(__fadd_rn(__fmul_rn(acc, gain), noise), baseline);
+    float v = __fmaf_rn(acc, gain, __fmaf_rn(z, sigma_e, baseline));
     v = fminf(fmaxf(v, lo), hi);
     return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
 }
@@ -190,18 +192,32 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId
     const float lo = (float)p.adc_min, hi = (float)p.adc_max;
     const int B = p.B;
     uint32_t* packed = reinterpret_cast<uint32_t*>(row);
-    for (int q = 0; 4 * q < B; ++q) {
+    const int n_full = B >> 2;                      // quads without a bounds check
+    for (int q = 0; q < n_full; ++q) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (sigma_e > 0.0f) {
             const u32x4 r = draw_block(t.key, STREAM_NOISE, (uint32_t)q);
             normal_pair(r.x, r.y, z[0], z[1]);
             normal_pair(r.z, r.w, z[2], z[3]);
         }
-        const int b = 4 * q;
+        int d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = digitise(row[4 * q + i], gain, z[i], sigma_e, baseline, lo, hi);
+        packed[2 * q] = (uint32_t)(d[0] & 0xffff) | ((uint32_t)d[1] << 16);
+        packed[2 * q + 1] = (uint32_t)(d[2] & 0xffff) | ((uint32_t)d[3] << 16);
+    }
+    if (B & 3) {                                     // last, partial quad
+        const int q = n_full, b = 4 * n_full;
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sigma_e > 0.0f) {
+            const u32x4 r = draw_block(t.key, STREAM_NOISE, (uint32_t)q);
+            normal_pair(r.x, r.y, z[0], z[1]);
+            normal_pair(r.z, r.w, z[2], z[3]);
+        }
         int d[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            d[i] = (b + i < B) ? digitise(row[b + i], gain, z[i] * sigma_e, baseline, lo, hi) : 0;
+            d[i] = (b + i < B) ? digitise(row[b + i], gain, z[i], sigma_e, baseline, lo, hi) : 0;
         packed[2 * q] = (uint32_t)(d[0] & 0xffff) | ((uint32_t)d[1] << 16);
         if (b + 2 < B) packed[2 * q + 1] = (uint32_t)(d[2] & 0xffff) | ((uint32_t)d[3] << 16);
     }

@@ -123,19 +123,23 @@ constexpr int STATS_FAST_WARPS = 8;
 constexpr int STATS_FLUSH_TRACES = 8192;      // 4 samples per lane per trace: 16-bit counters stay < 2^15
 
 struct StatsLane {
-    long long bs[4], bq[4];
+    long long bs[4], bq[4];          // per-bin sums, flushed from the 32-bit accumulators below
+    int bs32[4];
+    unsigned int bq32[4];
 };
 
+// Two samples of one 32-bit word.  Integer only: 1 add + 2 multiply-adds per sample for the sums, a
+// plain 16-bit read-modify-write of the lane-private histogram column.
 __device__ __forceinline__ void stats_word(const StatsArgs& a, uint32_t word, int slot, unsigned short* priv,
                                            unsigned int* hist_s, int win_lo, StatsLane& L, int& ts,
-                                           long long& tq) {
+                                           unsigned int& pq32) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int v = (int)(int16_t)(h ? (word >> 16) : (word & 0xffffu));
-        L.bs[slot + h] += v;
-        L.bq[slot + h] += (long long)v * v;
+        const int v = h ? ((int)word >> 16) : (int)(short)word;
+        L.bs32[slot + h] += v;
+        L.bq32[slot + h] += (unsigned int)(v * v);
+        pq32 += (unsigned int)(v * v);
         ts += v;
-        tq += (long long)v * v;
         if (a.adc_hist) {
             const unsigned w = (unsigned)(v - win_lo);
             if (w < (unsigned)STATS_WIN) priv[w * 32] += 1;
@@ -186,7 +190,7 @@ k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     const bool has0 = lane < wpr, has1 = lane + 32 < wpr;
     StatsLane L;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { L.bs[r] = 0; L.bq[r] = 0; }
+    for (int r = 0; r < 4; ++r) { L.bs[r] = 0; L.bq[r] = 0; L.bs32[r] = 0; L.bq32[r] = 0u; }
     const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
     const uint64_t n_events = a.n_traces / (uint64_t)a.P;
     const uint64_t n_items = (uint64_t)a.P * n_slices;
@@ -198,7 +202,8 @@ k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
         const uint64_t slice = item / (uint64_t)a.P;
         const uint64_t e_begin = slice * n_events / n_slices, e_end = (slice + 1) * n_events / n_slices;
         const long long charge_ref = (long long)a.B * llrintf(a.baseline[pixel]);
-        double pix_s = 0.0, pix_q = 0.0;
+        long long pix_s = 0;
+        double pix_q = 0.0;
         const uint32_t* base = cube + (uint64_t)pixel * wpr;
         // software pipeline: the words of the next STATS_T traces are in flight while the current
         // ones are processed (the first version was latency-bound: ~13 KB in flight per SM)
@@ -218,17 +223,16 @@ k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                 n0[tr] = (ok && has0) ? __ldcs(row + lane) : 0u;
                 n1[tr] = (ok && has1) ? __ldcs(row + lane + 32) : 0u;
             }
+            unsigned int pq32 = 0u;
 #pragma unroll
             for (int tr = 0; tr < STATS_T; ++tr) {
                 if (e + tr >= e_end) continue;
                 int ts = 0;
-                long long tq = 0;
-                if (has0) stats_word(a, w0[tr], 0, priv, hist_s, win_lo, L, ts, tq);
-                if (has1) stats_word(a, w1[tr], 2, priv, hist_s, win_lo, L, ts, tq);
+                if (has0) stats_word(a, w0[tr], 0, priv, hist_s, win_lo, L, ts, pq32);
+                if (has1) stats_word(a, w1[tr], 2, priv, hist_s, win_lo, L, ts, pq32);
                 if (a.pixel_sum || a.charge_hist) {
                     ts = __reduce_add_sync(0xffffffffu, ts);
-                    pix_s += (double)ts;
-                    if (a.pixel_sumsq) pix_q += (double)tq;                      // reduced once per item
+                    pix_s += ts;
                     if (a.charge_hist && lane == 0) {
                         long long bin = (long long)ts - charge_ref - a.charge_lo;
                         bin = bin < 0 ? 0 : (bin >= a.n_charge_bins ? a.n_charge_bins - 1 : bin);
@@ -237,6 +241,13 @@ k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                         else atomicAdd(a.charge_hist + bin, 1ull);
                     }
                 }
+            }
+            // widen the 32-bit accumulators (8 traces x 4 samples x v^2 < 2^32 for |v| <= 11585)
+            pix_q += (double)pq32;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                L.bs[r] += L.bs32[r]; L.bq[r] += L.bq32[r];
+                L.bs32[r] = 0; L.bq32[r] = 0u;
             }
 #pragma unroll
             for (int tr = 0; tr < STATS_T; ++tr) { w0[tr] = n0[tr]; w1[tr] = n1[tr]; }
@@ -255,7 +266,7 @@ k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
         if (a.pixel_sum) {
             pix_q = warp_sum(pix_q);
             if (lane == 0) {
-                atomicAdd(a.pixel_sum + pixel, pix_s);
+                atomicAdd(a.pixel_sum + pixel, (double)pix_s);
                 if (a.pixel_sumsq) atomicAdd(a.pixel_sumsq + pixel, pix_q);
             }
         }
