@@ -519,8 +519,11 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
     if (adc_hist && n_hist > 16384) return fail(DCT_E_UNSUPPORTED, "ADC histogram wider than 16384 bins");
     if (charge_hist && (a.B > 32 * dct::STATS_BINS_PER_LANE || n_charge_bins == 0))
         return fail(DCT_E_UNSUPPORTED, "charge histogram needs <= 128 bins per trace and n_charge_bins > 0");
-    // the fast kernel derives the power sums from the histogram, so it needs the histogram buffer
-    const bool fast = (a.B % 2 == 0) && a.B <= 128 && (reinterpret_cast<uintptr_t>(adc) & 3) == 0 &&
+    // the tile kernel derives the power sums from the histogram, so it needs the histogram buffer;
+    // every event's block of rows must start on a 16-byte boundary for cp.async
+    const int wpr = a.B / 2;
+    const bool fast = (a.B % 2 == 0) && a.B <= 128 && (reinterpret_cast<uintptr_t>(adc) & 15) == 0 &&
+                      ((uint64_t)a.P * wpr) % 4 == 0 && ((uint64_t)dct::STATS_ROWS * wpr) % 4 == 0 &&
                       (adc_hist != nullptr || moments == nullptr) && n_hist <= 16384 &&
                       std::max(std::abs(a.adc_min), std::abs(a.adc_max)) <= 11585;
     if (fast) {
@@ -530,16 +533,34 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
         int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
         charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));
-        const size_t smem = ((size_t)n_hist + dct::STATS_CHARGE_WIN +
-                             (size_t)dct::STATS_FAST_WARPS * dct::STATS_WIN * 16) * sizeof(unsigned int);
+        if (a.B > 64) {
+            // long traces: warp-per-trace variant (see stats.cuh)
+            const size_t smem = ((size_t)n_hist + dct::STATS_CHARGE_WIN +
+                                 (size_t)dct::STATS_FAST_WARPS * dct::STATS_WIN * 16) * sizeof(unsigned int);
+            if (smem > 48 * 1024)
+                CK(cudaFuncSetAttribute(dct::k_stats_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint64_t blocks = (uint64_t)h->sm_count * 3;
+            const uint64_t n_warps = blocks * dct::STATS_FAST_WARPS;
+            uint64_t n_slices = (4 * n_warps + a.P - 1) / a.P;
+            n_slices = std::max<uint64_t>(1, std::min<uint64_t>(n_slices, n_events));
+            dct::k_stats_warp<<<(unsigned)blocks, dct::STATS_FAST_WARPS * 32, smem, (cudaStream_t)stream>>>(
+                a, win_lo, (int)n_slices, charge_win_lo);
+            CK(cudaGetLastError());
+            return DCT_OK;
+        }
+        const size_t tile_words = ((size_t)dct::STATS_ROWS * wpr + 3) & ~(size_t)3;
+        const size_t smem = (2 * tile_words + (size_t)n_hist + dct::STATS_CHARGE_WIN +
+                             (size_t)(dct::STATS_ROWS / 32) * dct::STATS_WIN * 16) * sizeof(unsigned int);
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(dct::k_stats_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const uint64_t blocks = (uint64_t)h->sm_count * 3;
-        const uint64_t n_warps = blocks * dct::STATS_FAST_WARPS;
-        // (pixel, event-slice) work items: ~4 per warp for balance, never more slices than events
-        uint64_t n_slices = (4 * n_warps + a.P - 1) / a.P;
+            CK(cudaFuncSetAttribute(dct::k_stats_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+        const uint64_t n_pb = ((uint64_t)a.P + dct::STATS_ROWS - 1) / dct::STATS_ROWS;
+        uint64_t blocks = (uint64_t)h->sm_count * per_sm;
+        // (pixel block, event slice) work items: ~2 per CTA for balance, never more slices than events
+        uint64_t n_slices = (2 * blocks + n_pb - 1) / n_pb;
         n_slices = std::max<uint64_t>(1, std::min<uint64_t>(n_slices, n_events));
-        dct::k_stats_fast<<<(unsigned)blocks, dct::STATS_FAST_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        blocks = std::min<uint64_t>(blocks, n_pb * n_slices);
+        dct::k_stats_tile<<<(unsigned)blocks, dct::STATS_ROWS, smem, (cudaStream_t)stream>>>(
             a, win_lo, (int)n_slices, charge_win_lo);
         CK(cudaGetLastError());
         return DCT_OK;

@@ -108,17 +108,185 @@ k_stats(const StatsArgs a) {
     }
 }
 
-// Fast path (even B <= 128, 4-byte aligned cube).  ncu/CUDA-event history (profiles/r01): the first
-// K3 spent longer than K1 on the dark run -- plain shared-memory atomics serialise when every sample
-// sits within a few LSB of the pedestal, and float64 power sums cost ~25 instructions per sample.
-// This version
-//   * reads 32-bit words (two samples per lane per load), four traces in flight per warp;
-//   * gives every lane a private column hist[value - win_lo][lane] of 16-bit counters for the
-//     STATS_WIN values around the pedestal: no atomics, no races; samples outside the window use
-//     the CTA-wide atomic histogram;
-//   * keeps per-bin sums in 64-bit integers (one IMAD.WIDE each) and derives the raw power sums
-//     sum x^k from the CTA histogram when it is flushed, not per sample.
+// Fast path (even B <= 128, 16-byte aligned tiles, |adc| <= 11585).
+//
+// History (profiles/r01): v1 (warp = trace, shared-memory atomics + float64 power sums per sample)
+// took longer than K1 on the dark run; v2/v3 (lane-private histogram columns, per-pixel work items)
+// removed the atomics but still spent ~225 warp-instructions per trace because a warp only holds
+// 2-4 samples of a trace per lane.  This version turns the mapping around:
+//   * thread = trace.  A CTA owns a block of 128 consecutive pixels and walks a slice of events;
+//     each event's 128 rows are one contiguous run of the cube, brought into shared memory with
+//     16-byte cp.async (double buffered) and then read row-wise (odd word stride: conflict-free).
+//   * per sample: a plain 16-bit read-modify-write of the thread-private histogram column (window of
+//     STATS_WIN values around the pedestal; the rare sample outside goes to the CTA histogram with
+//     an atomic), and integer sums for the per-trace / per-pixel quantities.
+//   * per bin: warp-wide REDUX of the 32 rows, accumulated by lane (word % 32) in 64-bit registers.
+//   * per-pixel sums live in registers for the whole slice; raw power sums are derived from the
+//     CTA histogram when it is flushed.
 constexpr int STATS_WIN = 64;
+constexpr int STATS_ROWS = 128;               // traces per tile = threads per CTA
+constexpr int STATS_CHARGE_WIN = 1024;        // CTA-private window of the charge histogram
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(STATS_ROWS)
+k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
+    extern __shared__ __align__(16) unsigned int smem_u[];
+    const int n_hist = a.adc_max - a.adc_min + 1;
+    const int wpr = a.B >> 1;                                   // 32-bit words per trace
+    const int tile_words = (STATS_ROWS * wpr + 3) & ~3;
+    unsigned int* tile0 = smem_u;
+    unsigned int* tile1 = smem_u + tile_words;
+    unsigned int* hist_s = tile1 + tile_words;                  // [n_hist]
+    unsigned int* charge_s = hist_s + n_hist;                   // [STATS_CHARGE_WIN]
+    unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;      // my column: priv[w * 32]
+    for (int i = tid; i < n_hist + STATS_CHARGE_WIN + (STATS_ROWS / 32) * STATS_WIN * 16; i += STATS_ROWS)
+        hist_s[i] = 0u;
+    __syncthreads();
+
+    const uint64_t n_events = a.n_traces / (uint64_t)a.P;
+    const int n_pb = (a.P + STATS_ROWS - 1) / STATS_ROWS;
+    const uint64_t n_items = (uint64_t)n_pb * n_slices;
+    const uint64_t event_words = (uint64_t)a.P * wpr;
+    const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
+    long long bs[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};       // bins 2*lane, 2*lane+1, 2*(lane+32), +1
+    int my_samples = 0;
+
+    for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pb = (int)(item % (uint64_t)n_pb);
+        const uint64_t slice = item / (uint64_t)n_pb;
+        const uint64_t e_begin = slice * n_events / n_slices, e_end = (slice + 1) * n_events / n_slices;
+        const int p0 = pb * STATS_ROWS;
+        const int np = min(STATS_ROWS, a.P - p0);                // rows in this block
+        const int n_vec = (np * wpr + 3) >> 2;                   // 16-byte pieces per tile (tail padded)
+        const bool mine = tid < np;
+        const int pixel = p0 + tid;
+        const long long charge_ref = mine ? (long long)a.B * llrintf(a.baseline[pixel]) : 0;
+        long long pix_s = 0, pix_q = 0;
+        const uint32_t* src0 = cube + (uint64_t)p0 * wpr;
+
+        if (e_begin < e_end) {
+            const uint32_t* src = src0 + e_begin * event_words;
+            for (int v = tid; v < n_vec; v += STATS_ROWS) cp_async16(tile0 + 4 * v, src + 4 * v);
+            cp_async_commit();
+        }
+        for (uint64_t e = e_begin; e < e_end; ++e) {
+            unsigned int* cur = ((e - e_begin) & 1) ? tile1 : tile0;
+            unsigned int* nxt = ((e - e_begin) & 1) ? tile0 : tile1;
+            cp_async_wait_all();
+            __syncthreads();                                     // tile e landed; tile e-1 fully consumed
+            if (e + 1 < e_end) {
+                const uint32_t* src = src0 + (e + 1) * event_words;
+                for (int v = tid; v < n_vec; v += STATS_ROWS) cp_async16(nxt + 4 * v, src + 4 * v);
+                cp_async_commit();
+            }
+            const unsigned int* row = cur + tid * wpr;
+            int ts = 0;
+            unsigned int tq = 0;
+            for (int w = 0; w < wpr; ++w) {
+                const unsigned int word = mine ? row[w] : 0u;
+                const int v0 = (int)(short)word, v1 = (int)word >> 16;
+                const unsigned int q0 = (unsigned int)(v0 * v0), q1 = (unsigned int)(v1 * v1);
+                ts += v0 + v1;
+                tq += q0 + q1;
+                if (a.adc_hist && mine) {
+                    const unsigned h0 = (unsigned)(v0 - win_lo), h1 = (unsigned)(v1 - win_lo);
+                    if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else atomicAdd(&hist_s[v0 - a.adc_min], 1u);
+                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else atomicAdd(&hist_s[v1 - a.adc_min], 1u);
+                }
+                if (a.bin_sum) {
+                    // column sums over the warp's 32 rows; lane (w % 32) keeps the bins of word w
+                    const int s0 = __reduce_add_sync(0xffffffffu, v0), s1 = __reduce_add_sync(0xffffffffu, v1);
+                    const unsigned int r0 = __reduce_add_sync(0xffffffffu, q0), r1 = __reduce_add_sync(0xffffffffu, q1);
+                    if (lane == (w & 31)) {
+                        if (w < 32) { bs[0] += s0; bs[1] += s1; bq[0] += r0; bq[1] += r1; }
+                        else        { bs[2] += s0; bs[3] += s1; bq[2] += r0; bq[3] += r1; }
+                    }
+                }
+            }
+            if (mine) {
+                pix_s += ts;
+                pix_q += tq;
+                if (a.charge_hist) {
+                    long long bin = (long long)ts - charge_ref - a.charge_lo;
+                    bin = bin < 0 ? 0 : (bin >= a.n_charge_bins ? a.n_charge_bins - 1 : bin);
+                    const long long cw = bin - charge_win_lo;
+                    if (cw >= 0 && cw < STATS_CHARGE_WIN) atomicAdd(&charge_s[cw], 1u);
+                    else atomicAdd(a.charge_hist + bin, 1ull);
+                }
+            }
+            my_samples += a.B;
+            if (a.adc_hist && my_samples >= 60000) {             // 16-bit columns: fold this warp's window
+                __syncwarp();
+                for (int w = 0; w < STATS_WIN; ++w) {
+                    const unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)priv[w * 32]);
+                    priv[w * 32] = 0;
+                    const int v = win_lo + w - a.adc_min;
+                    if (lane == 0 && c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+                }
+                my_samples = 0;
+            }
+        }
+        __syncthreads();                                         // last tile consumed before the next item loads
+        if (mine && a.pixel_sum) {
+            atomicAdd(a.pixel_sum + pixel, (double)pix_s);
+            if (a.pixel_sumsq) atomicAdd(a.pixel_sumsq + pixel, (double)pix_q);
+        }
+    }
+    const int bins[4] = {2 * lane, 2 * lane + 1, 2 * (lane + 32), 2 * (lane + 32) + 1};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (bins[r] < a.B && (bs[r] | bq[r])) {
+            if (a.bin_sum) atomicAdd(a.bin_sum + bins[r], (double)bs[r]);
+            if (a.bin_sumsq) atomicAdd(a.bin_sumsq + bins[r], (double)bq[r]);
+        }
+    __syncthreads();
+    if (a.adc_hist) {
+        // fold every thread-private column into the CTA histogram
+        for (int i = tid; i < (STATS_ROWS / 32) * STATS_WIN; i += STATS_ROWS) {
+            const unsigned short* col = priv_all + (size_t)i * 32;
+            unsigned int c = 0;
+            for (int l = 0; l < 32; ++l) c += col[(l + tid) & 31];
+            const int v = win_lo + (i % STATS_WIN) - a.adc_min;
+            if (c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+        }
+        __syncthreads();
+    }
+    if (a.charge_hist)
+        for (int i = tid; i < STATS_CHARGE_WIN; i += STATS_ROWS) {
+            const unsigned int c = charge_s[i];
+            if (c && charge_win_lo + i < a.n_charge_bins) atomicAdd(a.charge_hist + charge_win_lo + i, (unsigned long long)c);
+        }
+    // flush the CTA histogram; the raw power sums come from it (exact: integers < 2^53 per CTA)
+    double m[4] = {0, 0, 0, 0};
+    if (a.adc_hist) {
+        for (int i = tid; i < n_hist; i += STATS_ROWS) {
+            const unsigned int c = hist_s[i];
+            if (c) {
+                atomicAdd(a.adc_hist + i, (unsigned long long)c);
+                const double x = (double)(i + a.adc_min), cd = (double)c;
+                m[0] += cd * x; m[1] += cd * x * x; m[2] += cd * x * x * x; m[3] += cd * x * x * x * x;
+            }
+        }
+    }
+    if (a.moments && a.adc_hist) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = warp_sum(m[k]);
+            if (lane == 0 && v != 0.0) atomicAdd(a.moments + k, v);
+        }
+    }
+}
+
+// ---- warp-per-trace variant (v3), kept for long traces (B > 64) where the tile kernel's
+// shared-memory footprint leaves too few warps per SM (dark.yml: 5.7 ms vs 8.5 ms per 16384 events)
 constexpr int STATS_FAST_WARPS = 8;
 constexpr int STATS_FLUSH_TRACES = 8192;      // 4 samples per lane per trace: 16-bit counters stay < 2^15
 
@@ -165,14 +333,15 @@ __device__ __forceinline__ void stats_fold_private(unsigned short* priv_all, uns
 }
 
 constexpr int STATS_T = 8;                    // traces per pipeline stage
-constexpr int STATS_CHARGE_WIN = 1024;       // CTA-private window of the charge histogram
+// (window sizes shared with the tile kernel)
+//      // CTA-private window of the charge histogram
 
 // Work item = (pixel, slice of events): a warp walks the traces of ONE pixel, so the per-pixel sums
 // stay in registers and are flushed with two atomics per item (the first version issued three
 // global atomics per trace onto a few hundred hot addresses and was bound by L2 atomic
 // serialisation: 8-11 ms per 2 GB cube instead of ~1 ms).
 __global__ void __launch_bounds__(STATS_FAST_WARPS * 32, 3)
-k_stats_fast(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
+k_stats_warp(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     extern __shared__ unsigned int smem_u[];
     const int n_hist = a.adc_max - a.adc_min + 1;
     unsigned int* hist_s = smem_u;                                               // [n_hist]
