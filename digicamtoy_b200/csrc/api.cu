@@ -18,6 +18,7 @@
 #include "replay.cuh"
 #include "stats.cuh"
 #include "selftest.cuh"
+#include "dump.cuh"
 
 namespace {
 
@@ -585,6 +586,26 @@ int dct_write_calibrate(int16_t* buf, size_t n, void* stream) {
     const size_t n_vec = n / 8, n_tail = n - n_vec * 8;
     dct::k_write_calibrate<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<int4*>(buf), n_vec, buf + n_vec * 8, n_tail);
+    CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, uint32_t max_pe,
+                 int32_t* n_pe, double* pe_time, float* pe_amp, float* noise, void* stream) {
+    if (!h || !n_pe) return fail(DCT_E_ARG, "handle or n_pe is NULL");
+    if (max_pe > 0 && (!pe_time || !pe_amp)) return fail(DCT_E_ARG, "pe_time / pe_amp is NULL");
+    if (n_events == 0) return DCT_OK;
+    CK(cudaSetDevice(h->device));
+    dct::DumpArgs d;
+    d.g.p = h->p;
+    d.g.k0 = (uint32_t)seed; d.g.k1 = (uint32_t)(seed >> 32);
+    d.g.first_event = first_event;
+    d.g.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
+    d.g.adc = nullptr; d.g.sig_time = nullptr; d.g.sig_charge = nullptr; d.g.table_in_smem = 0;
+    d.max_pe = max_pe; d.n_pe = n_pe; d.pe_time = pe_time; d.pe_amp = pe_amp; d.noise = noise;
+    const uint64_t blocks = (d.g.n_traces + 127) / 128;
+    if (blocks > 0x7fffffffull) return fail(DCT_E_ARG, "too many traces for one launch");
+    dct::k_dump_pe<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(d);
     CK(cudaGetLastError());
     return DCT_OK;
 }

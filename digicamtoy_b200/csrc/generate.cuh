@@ -193,6 +193,7 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId
     const int B = p.B;
     uint32_t* packed = reinterpret_cast<uint32_t*>(row);
     const int n_full = B >> 2;                      // quads without a bounds check
+#pragma unroll 2
     for (int q = 0; q < n_full; ++q) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (sigma_e > 0.0f) {

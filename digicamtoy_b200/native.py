@@ -24,7 +24,7 @@ KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 's
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',
     'dct_generate', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
-    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample',
+    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe',
 )
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -83,6 +83,7 @@ def load_library():
         f.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dct_stats_accumulate.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
     lib.dct_write_calibrate.argtypes = [vp, ctypes.c_size_t, vp]
+    lib.dct_trace_pe.argtypes = [vp, u64, u64, u32, u32, vp, vp, vp, vp, vp]
     lib.dct_test_sample.argtypes = [u32, ctypes.c_double, ctypes.c_double, u64, u32, vp, vp]
     for name in EXPORTED_SYMBOLS:
         if name not in ('dct_last_error', 'dct_destroy'):
@@ -159,6 +160,11 @@ class Handle:
         fn = self.lib.dct_replay_f64 if precision == 'f64' else self.lib.dct_replay_f32
         check(fn(self.ptr, n_events, offsets_ptr, time_ptr, amp_ptr, sig_time_ptr, sig_amp_ptr,
                  noise_ptr, adc_ptr, clamped_ptr, stream))
+
+    def trace_pe(self, seed, first_event, n_events, max_pe, n_pe_ptr, pe_time_ptr=None, pe_amp_ptr=None,
+                 noise_ptr=None, stream=None):
+        check(self.lib.dct_trace_pe(self.ptr, seed, first_event, n_events, max_pe, n_pe_ptr, pe_time_ptr,
+                                    pe_amp_ptr, noise_ptr, stream))
 
     def stats_accumulate(self, adc_ptr, n_events, adc_hist=None, bin_sum=None, bin_sumsq=None,
                          pixel_sum=None, pixel_sumsq=None, charge_hist=None, charge_lo=0,

@@ -12,7 +12,8 @@ Deliberate differences from the reference:
   * ``voltage_drop`` scales ``n_photon`` per pixel (the reference broadcasts (P,1)x(P,) to (P,P)).
   * ``poisson=False`` uses ``round(n_photon)`` primaries (the reference raises on floats and
     lets the configured value grow from event to event).
-  * the pe lists ``nsb_time / nsb_photon / mask`` never exist on the GPU path and are not exposed.
+  * the pe lists ``nsb_time / nsb_photon / mask`` are not stored by the generation kernels; reading
+    them re-derives the current event's lists from the counter-based RNG (``trace_pe``).
 """
 from __future__ import annotations
 
@@ -152,11 +153,43 @@ class NTraceGenerator:
         self.sampling_bins = self.params.sampling_bins
 
     def __getattr__(self, name):
-        if name in ('nsb_time', 'nsb_photon', 'mask'):
-            raise AttributeError(
-                '{} is not materialised: photo-electrons live in GPU registers only '
-                '(use the oracle in oracle/reference_port.py to inspect pe lists)'.format(name))
+        # nsb_time / nsb_photon / mask (:248-257, :345-348) are never stored by the generation
+        # kernels; on access they are re-derived for the current event from the same counters.
+        if name in ('nsb_time', 'nsb_photon', 'mask') and 'count' in self.__dict__:
+            if self.count < 0:
+                P = self.params.n_pixels
+                return {'nsb_time': np.zeros((P, 1)), 'nsb_photon': np.zeros((P, 1)),
+                        'mask': np.zeros((P, 1))}[name]
+            pe = self.trace_pe(1, first_event=self.first_event + self.count, noise=False)
+            time, amp, n = pe['time'][0], pe['amplitude'][0], pe['count'][0]
+            mask = (np.arange(time.shape[1])[None, :] < n[:, None]).astype(int)
+            return {'nsb_time': time, 'nsb_photon': amp, 'mask': mask}[name]
         raise AttributeError(name)
+
+    def trace_pe(self, n_events, first_event=None, noise=True):
+        """NSB photo-electron clusters (and electronic noise) behind the traces of the given events,
+        re-derived from the counter-based RNG: ``count (n,P)``, ``time (n,P,M) f64``,
+        ``amplitude (n,P,M) f32`` (zero-padded), ``noise (n,P,B) f32``."""
+        torch = _torch()
+        p = self.params
+        n_events = int(n_events)
+        if first_event is None:
+            first_event = self.first_event
+        dev = torch.device('cuda', self.device)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        count = torch.zeros((n_events, p.n_pixels), dtype=torch.int32, device=dev)
+        self._handle.trace_pe(self.seed, int(first_event), n_events, 0, count.data_ptr(), stream=stream)
+        m = max(1, int(count.max().item())) if n_events else 1
+        time = torch.zeros((n_events, p.n_pixels, m), dtype=torch.float64, device=dev)
+        amp = torch.zeros((n_events, p.n_pixels, m), dtype=torch.float32, device=dev)
+        nz = torch.zeros((n_events, p.n_pixels, p.n_bins), dtype=torch.float32, device=dev) if noise else None
+        self._handle.trace_pe(self.seed, int(first_event), n_events, m, count.data_ptr(), time.data_ptr(),
+                              amp.data_ptr(), nz.data_ptr() if noise else None, stream)
+        torch.cuda.synchronize(dev)
+        out = dict(count=count.cpu().numpy(), time=time.cpu().numpy(), amplitude=amp.cpu().numpy())
+        if noise:
+            out['noise'] = nz.cpu().numpy()
+        return out
 
     # ------------------------------------------------------------------ bulk API (device / host)
     def generate(self, n_events, first_event=None, out=None, truth=False, stream=None):

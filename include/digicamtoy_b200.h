@@ -153,6 +153,18 @@ DCT_API int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_e
  * generator uses.  Its GB/s is the practical ceiling of the HBM-write roofline. */
 DCT_API int dct_write_calibrate(int16_t* buf, size_t n, void* stream);
 
+/* The photo-electron lists and noise values behind the traces of events [first_event, +n_events):
+ * what the reference leaves in nsb_time / nsb_photon (x mask) after next() (:248-257, :345-348).
+ * Counter-based RNG: this re-derives exactly what dct_generate consumed for the same
+ * (seed, event, pixel).  Call once with max_pe = 0 to get the counts, then with max_pe >= max count.
+ *   n_pe     device int32  [n_events, P]           clusters per trace (always written)
+ *   pe_time  device double [n_events, P, max_pe]   absolute time in ns       (first n_pe valid)
+ *   pe_amp   device float  [n_events, P, max_pe]   smeared cluster amplitude (first n_pe valid)
+ *   noise    device float  [n_events, P, B]        electronic noise of the kept bins, or NULL   */
+DCT_API int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
+                         uint32_t max_pe, int32_t* n_pe, double* pe_time, float* pe_amp, float* noise,
+                         void* stream);
+
 /* Test hook (not on the product path): n draws of one device sampler into device float out[n].
  * kind: 0 normal, 1 exponential gap (a = mean), 2 Borel(a), 3 Poisson(a), 4 total progeny of
  * b primaries with Poisson(a) offspring, 5 uniform [0,1). */

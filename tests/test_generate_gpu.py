@@ -318,7 +318,7 @@ def test_iterator_surface():
                     time_signal=[[0, 100], [20, 50, 100], [0, 100]], gain=[10, 10, 29], seed=1), 5)
     assert all(np.array_equal(s[1], bulk[i]) for i, s in enumerate(seen))   # batching is invisible
     with pytest.raises(AttributeError):
-        toy.nsb_time
+        toy.no_such_attribute
     assert toy.true_baseline.shape == (3,) and toy.tau > 17
 
 
@@ -351,3 +351,46 @@ def test_write_calibrate_kernel():
     native.write_calibrate(buf.data_ptr(), buf.numel())
     torch.cuda.synchronize()
     assert int((buf < 0).sum()) == 0
+
+
+# ------------------------------------------------------------------ closing the loop: GPU pe lists -> reference arithmetic
+@pytest.mark.parametrize('kernel', ['scatter', 'sweep'])
+@pytest.mark.parametrize('rate,npe', [(1.0, 100.), (0.125, 10.), (0.003, 2.)])
+def test_reference_arithmetic_on_gpu_drawn_photoelectrons_reproduces_gpu_adc(kernel, rate, npe):
+    """The stochastic kernels never store their photo-electrons; trace_pe re-derives them from the
+    same Philox counters.  Feeding those lists, the pulse truth and the noise through the ORACLE's
+    shaping + digitisation (float64, the reference's own arithmetic, reference :350-381) must give
+    the ADC counts the GPU wrote: every stage of K1 checked against the reference on identical
+    draws.  float32 accumulation on the GPU -> at most 1 LSB on rounding ties."""
+    P = 160
+    kw = dict(n_pixels=P, nsb_rate=rate, n_photon=npe, **ACDC)
+    g = gen(seed=321, kernel=kernel, saturate=None, **kw)
+    n_ev = 6
+    adc, t, q = cube(g, n_ev, truth=True)
+    pe = g.trace_pe(n_ev, first_event=0)
+    cfg = orc.make_config(**kw)
+    assert pe['count'].mean() == pytest.approx(rate * 240, rel=0.05)
+    n_diff = 0
+    for e in range(n_ev):
+        want = orc.shape_and_digitise(cfg, pe['time'][e], pe['amplitude'][e].astype(np.float64),
+                                      t[e].astype(np.float64), q[e].astype(np.float64),
+                                      pe['noise'][e].astype(np.float64))
+        d = np.abs(adc[e].astype(np.int64) - want.astype(np.int64))
+        assert d.max() <= 1, d.max()
+        n_diff += int((d != 0).sum())
+    assert n_diff <= 2e-3 * adc.size, n_diff
+
+
+def test_pe_list_attributes_of_the_iterator():
+    toy = gen(n_pixels=20, nsb_rate=0.3, n_photon=3., n_events=3, seed=8, **ACDC)
+    assert toy.nsb_time.shape == (20, 1) and not toy.mask.any()          # before the first event (:194-196)
+    for ev in toy:
+        t, a, m = ev.nsb_time, ev.nsb_photon, ev.mask
+        assert t.shape == a.shape == m.shape and t.shape[0] == 20
+        n = m.sum(axis=1)
+        assert abs(n.mean() - 0.3 * 240) < 5 * np.sqrt(72 / 20)
+        for p in range(20):
+            tt = t[p, :n[p]]
+            assert np.all(np.diff(tt) >= 0) and tt.min() >= -40 and tt.max() < 200   # sorted, inside the window
+            assert np.all(a[p, n[p]:] == 0)
+        assert abs(a[m.astype(bool)].mean() - 1 / (1 - 0.08)) < 0.1
