@@ -160,6 +160,26 @@ class ClockSampler:
                     power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs next to its GPU before any pinned buffer is allocated, so that the
+    D2H copies of the end-to-end path do not cross the socket interconnect (8 ranks on one box share
+    host memory bandwidth; first-touch puts the pinned pages on the local node)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:      # match by PCI address: NVML and CUDA may enumerate in different orders
+            import torch
+            pr = torch.cuda.get_device_properties(index)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(
+                '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:      # no NVML, restricted cpuset, ...: keep the inherited affinity
+        return 'unchanged (%s)' % type(e).__name__
+
+
 # --------------------------------------------------------------------------------- the B200 arm
 def run_b200_arm(a):
     import torch
@@ -174,6 +194,7 @@ def run_b200_arm(a):
         raise SystemExit('bench.py: no CUDA device; the B200 arm has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    cpus = bind_to_gpu_numa_node(local) if world > 1 else 'all'
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -249,7 +270,8 @@ def run_b200_arm(a):
             h_ms = float(t.item())
         e2e = dict(value=samples_per_step * n_e2e / (h_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=0,
                    d2h_bytes_per_step=E * P * B * 2, steps=n_e2e, ms_per_step=h_ms / n_e2e,
-                   api='NTraceGenerator.generate_host -> dct_generate_host (pinned host buffer, chunked D2H overlapped with generation)')
+                   api='NTraceGenerator.generate_host -> dct_generate_host (pinned host buffer, chunked D2H overlapped with generation)',
+                   host_cpus_rank0=(cpus if isinstance(cpus, str) else '%d cpus: %s..%s' % (len(cpus), cpus[0], cpus[-1])))
         del host
     if rank == 0:
         clocks.stop()

@@ -183,3 +183,18 @@ SAMPLERS = {'normal': 0, 'exp_gap': 1, 'borel': 2, 'poisson': 3, 'branching': 4,
 
 def test_sample(kind, a, b, seed, n, out_ptr, stream=None):
     check(load_library().dct_test_sample(SAMPLERS[kind], float(a), float(b), seed, n, out_ptr, stream))
+
+
+def export_config(params, path, adc_min=0, adc_max=4095, kernel=KERNEL_AUTO):
+    """Flat binary dump of a dct_config for non-Python consumers (examples/c_abi_demo.c):
+    10 x uint32 scalars, 3 x float64 (t0, t_end, dt), then every array as float64."""
+    head = np.array([params.n_pixels, params.n_pulses, params.n_bins, params.n_drop, len(params.knot_x),
+                     int(params.poisson), max(0, int(params.sub_binning)), np.int32(adc_min).astype(np.uint32),
+                     np.int32(adc_max).astype(np.uint32), kernel], dtype=np.uint32)
+    with open(path, 'wb') as f:
+        f.write(head.tobytes())
+        f.write(np.array([params.time_start, params.time_end, params.time_sampling], dtype=np.float64).tobytes())
+        for a in (params.nsb_rate, params.crosstalk, params.gain, params.sigma_1, params.sigma_e,
+                  params.baseline, params.n_photon, params.time_signal, params.jitter, params.knot_x,
+                  params.coef):
+            f.write(_f64(a).tobytes())
