@@ -28,7 +28,7 @@ constexpr int SWEEP_PHASES = 8;           // 4 ns sampling / 0.5 ns knots
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_MAX_BINS = 256;
 constexpr int SWEEP_GROUP = 4;            // taps per skip group
-constexpr double SWEEP_MIN_MEAN_PE = 24.0;   // below this the scatter kernel wins (few pe per trace)
+constexpr double SWEEP_MIN_MEAN_PE = 0.0;    // measured (scripts/kernel_crossover.py): sweep >= scatter at every rate, 0.7 .. 240 pe / trace
 
 inline bool sweep_supported(const DevParams& p) {
     return p.n_phase == SWEEP_PHASES && p.n_taps == SWEEP_TAPS && p.sub_binning <= 0 &&

@@ -43,11 +43,12 @@ enum {
     DCT_E_NOMEM = -4
 };
 
-/* Kernel selection for dct_generate (DCT_KERNEL_AUTO picks by mean pe count per trace). */
+/* Kernel selection for dct_generate.  DCT_KERNEL_AUTO: the sweep kernel whenever the configuration
+ * supports it (22-tap / 8-phase polyphase table, continuous NSB), else the scatter kernel. */
 enum {
     DCT_KERNEL_AUTO = 0,
     DCT_KERNEL_SCATTER = 1,  /* shared-memory accumulators, any template / sampling           */
-    DCT_KERNEL_SWEEP = 2     /* time-ordered register window, high NSB rates                  */
+    DCT_KERNEL_SWEEP = 2     /* time-ordered register window (default template at 4 ns sampling) */
 };
 
 /* Everything NTraceGenerator.__init__ derives (reference :52-157), already transformed on the
