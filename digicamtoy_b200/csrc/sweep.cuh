@@ -27,7 +27,16 @@ constexpr int SWEEP_TAPS = 22;            // 88 ns template / 4 ns sampling
 constexpr int SWEEP_PHASES = 8;           // 4 ns sampling / 0.5 ns knots
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_MAX_BINS = 256;
-constexpr int SWEEP_GROUP = 4;            // taps per skip group
+#ifndef DCT_SWEEP_GROUP
+#define DCT_SWEEP_GROUP 4
+#endif
+#ifndef DCT_SWEEP_UNROLL2
+#define DCT_SWEEP_UNROLL2 1
+#endif
+#ifndef DCT_SWEEP_MIN_BLOCKS
+#define DCT_SWEEP_MIN_BLOCKS 6
+#endif
+constexpr int SWEEP_GROUP = DCT_SWEEP_GROUP;   // taps per skip group (even)
 constexpr double SWEEP_MIN_MEAN_PE = 0.0;    // measured (scripts/kernel_crossover.py): sweep >= scatter at every rate, 0.7 .. 240 pe / trace
 
 inline bool sweep_supported(const DevParams& p) {
@@ -71,7 +80,7 @@ __device__ __forceinline__ void slide_window(float (&W)[TAPS], bool go) {
 }
 
 template <int TAPS, int PHASES, int NT>
-__global__ void __launch_bounds__(NT, 6)
+__global__ void __launch_bounds__(NT, DCT_SWEEP_MIN_BLOCKS)
 k_generate_sweep(const GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevParams& p = a.p;
@@ -109,11 +118,8 @@ k_generate_sweep(const GenArgs a) {
             const int kb_shift = 1 - p.n_drop;               // kept index of W[0] = cell + kb_shift
             const int first_needed = p.n_drop - 1;           // tap j is kept iff j >= first_needed - cell
             const int last_needed = p.n_drop + B - 1;        //             and j <  last_needed  - cell
-            for (uint32_t i = 0;; ++i) {
-                const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                elapsed += gap;
-                if (elapsed >= p.span) break;
+            // One photo-electron: slide the window to its cell, then add its taps.
+            auto add_pe = [&](const u32x4& r, float gap) {
                 int kb = cell + kb_shift;
                 int k = advance_onset(p, gap, cell, off);
                 // slide by one cell: predicated, all lanes
@@ -162,7 +168,31 @@ k_generate_sweep(const GenArgs a) {
                         }
                     }
                 }
+            };
+#if DCT_SWEEP_UNROLL2
+            // two photo-electrons per iteration: their Philox blocks and samplers are independent
+            // and overlap; the window updates stay in order
+            for (uint32_t i = 0;; i += 2) {
+                const u32x4 ra = draw_block(t.key, STREAM_NSB, i);
+                const u32x4 rb = draw_block(t.key, STREAM_NSB, i + 1);
+                const float gap_a = exp_gap(ra.x, q.neg_ln2_over_rate);
+                const float gap_b = exp_gap(rb.x, q.neg_ln2_over_rate);
+                elapsed += gap_a;
+                if (elapsed >= p.span) break;
+                add_pe(ra, gap_a);
+                elapsed += gap_b;
+                if (elapsed >= p.span) break;
+                add_pe(rb, gap_b);
             }
+#else
+            for (uint32_t i = 0;; ++i) {
+                const u32x4 r = draw_block(t.key, STREAM_NSB, i);
+                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
+                elapsed += gap;
+                if (elapsed >= p.span) break;
+                add_pe(r, gap);
+            }
+#endif
             // retire what is left in the window
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
