@@ -134,6 +134,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void red_shared_inc(unsigned int smem_addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_addr) : "memory");
+}
+
 __global__ void __launch_bounds__(STATS_ROWS)
 k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     extern __shared__ __align__(16) unsigned int smem_u[];
@@ -157,6 +161,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     const uint64_t event_words = (uint64_t)a.P * wpr;
     const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
     long long bs[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};       // bins 2*lane, 2*lane+1, 2*(lane+32), +1
+    const unsigned int hist_addr = (unsigned int)__cvta_generic_to_shared(hist_s) - 4u * (unsigned int)a.adc_min;
     int my_samples = 0;
 
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -190,6 +195,8 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             const unsigned int* row = cur + tid * wpr;
             int ts = 0;
             unsigned int tq = 0;
+            int cs[4] = {0, 0, 0, 0};                            // this event's column sums (one word per slot)
+            unsigned int cq[4] = {0u, 0u, 0u, 0u};
             for (int w = 0; w < wpr; ++w) {
                 const unsigned int word = mine ? row[w] : 0u;
                 const int v0 = (int)(short)word, v1 = (int)word >> 16;
@@ -198,19 +205,21 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                 tq += q0 + q1;
                 if (a.adc_hist && mine) {
                     const unsigned h0 = (unsigned)(v0 - win_lo), h1 = (unsigned)(v1 - win_lo);
-                    if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else atomicAdd(&hist_s[v0 - a.adc_min], 1u);
-                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else atomicAdd(&hist_s[v1 - a.adc_min], 1u);
+                    if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v0);
+                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v1);
                 }
                 if (a.bin_sum) {
                     // column sums over the warp's 32 rows; lane (w % 32) keeps the bins of word w
                     const int s0 = __reduce_add_sync(0xffffffffu, v0), s1 = __reduce_add_sync(0xffffffffu, v1);
                     const unsigned int r0 = __reduce_add_sync(0xffffffffu, q0), r1 = __reduce_add_sync(0xffffffffu, q1);
                     if (lane == (w & 31)) {
-                        if (w < 32) { bs[0] += s0; bs[1] += s1; bq[0] += r0; bq[1] += r1; }
-                        else        { bs[2] += s0; bs[3] += s1; bq[2] += r0; bq[3] += r1; }
+                        if (w < 32) { cs[0] = s0; cs[1] = s1; cq[0] = r0; cq[1] = r1; }
+                        else        { cs[2] = s0; cs[3] = s1; cq[2] = r0; cq[3] = r1; }
                     }
                 }
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { bs[r] += cs[r]; bq[r] += cq[r]; }
             if (mine) {
                 pix_s += ts;
                 pix_q += tq;
