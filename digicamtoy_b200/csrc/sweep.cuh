@@ -33,6 +33,9 @@ constexpr int SWEEP_MAX_BINS = 256;
 #ifndef DCT_SWEEP_UNROLL2
 #define DCT_SWEEP_UNROLL2 1
 #endif
+#ifndef DCT_SWEEP_HOIST_KEYS
+#define DCT_SWEEP_HOIST_KEYS 0
+#endif
 #ifndef DCT_SWEEP_MIN_BLOCKS
 #define DCT_SWEEP_MIN_BLOCKS 6
 #endif
@@ -169,12 +172,20 @@ k_generate_sweep(const GenArgs a) {
                     }
                 }
             };
+#if DCT_SWEEP_HOIST_KEYS
+            const PhiloxKeys ks = philox_keys(t.key.k0, t.key.k1);
+            u32x4 ctr;
+            ctr.y = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu); ctr.z = t.key.pixel; ctr.w = t.key.ev_lo;
+            auto draw_nsb = [&](uint32_t i) { u32x4 c = ctr; c.x = i; return philox4x32_keyed(c, ks); };
+#else
+            auto draw_nsb = [&](uint32_t i) { return draw_block(t.key, STREAM_NSB, i); };
+#endif
 #if DCT_SWEEP_UNROLL2
             // two photo-electrons per iteration: their Philox blocks and samplers are independent
             // and overlap; the window updates stay in order
             for (uint32_t i = 0;; i += 2) {
-                const u32x4 ra = draw_block(t.key, STREAM_NSB, i);
-                const u32x4 rb = draw_block(t.key, STREAM_NSB, i + 1);
+                const u32x4 ra = draw_nsb(i);
+                const u32x4 rb = draw_nsb(i + 1);
                 const float gap_a = exp_gap(ra.x, q.neg_ln2_over_rate);
                 const float gap_b = exp_gap(rb.x, q.neg_ln2_over_rate);
                 elapsed += gap_a;
