@@ -28,6 +28,11 @@ def _drop(coefficients, rate_hz):
     return value * (rate_hz < 1.4e9)
 
 
+def gain_drop(nsb_rate, cell_capacitance=85. * 1E-15, bias_resistance=10. * 1E3):
+    """Simple RC gain-drop model (reference utils/analytical.py:4-6); not used by the generator."""
+    return 1. / (1. + np.asarray(nsb_rate, dtype=np.float64) * cell_capacitance * bias_resistance * 1E9)
+
+
 def true_gain_drop(nsb_rate_hz):
     return _drop(_GAIN_DROP, nsb_rate_hz)
 

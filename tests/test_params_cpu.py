@@ -107,3 +107,20 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_analytical_shim_matches_reference_polynomials():
+    """reference utils/analytical.py:9-37: cubic polynomials in the NSB rate [Hz], zero from 1.4 GHz."""
+    from digicamtoy.utils import analytical as an
+    nsb = np.array([0.0, 1e8, 5e8, 1.39e9, 1.4e9, 2e9])
+    want_gain = (1.0000 - 4.16866e-10 * nsb + 2.27832e-19 * nsb ** 2 - 6.05033e-29 * nsb ** 3) * (nsb < 1.4e9)
+    want_xt = (1. - 7.41234e-10 * nsb + 4.60472e-19 * nsb ** 2 - 1.28336e-28 * nsb ** 3) * (nsb < 1.4e9)
+    want_pde = (1. - 2.2929e-10 * nsb + 9.59912e-20 * nsb ** 2 - 2.22249e-29 * nsb ** 3) * (nsb < 1.4e9)
+    assert np.allclose(an.true_gain_drop(nsb), want_gain, rtol=1e-14, atol=0)
+    assert np.allclose(an.true_xt_drop(nsb), want_xt, rtol=1e-14, atol=0)
+    assert np.allclose(an.true_pde_drop(nsb), want_pde, rtol=1e-14, atol=0)
+    assert an.true_gain_drop(1.4e9) == 0 and an.true_gain_drop(0.0) == 1.0
+    assert np.allclose(an.gain_drop(np.array([0., 1e9])), [1.0, 1 / (1 + 85e-15 * 10e3 * 1e9 * 1e9)])
+    z, _ = load_golden('voltage_drop_refbug')      # the reference's own evaluation of the polynomials
+    p = params.build_params(n_pixels=5, nsb_rate=0.4, voltage_drop=True, n_photon=20., jitter=1.0)
+    assert np.allclose(p.gain, z['gain'], rtol=1e-14) and np.allclose(p.crosstalk, z['crosstalk'], rtol=1e-14)
