@@ -394,3 +394,20 @@ def test_pe_list_attributes_of_the_iterator():
             assert np.all(np.diff(tt) >= 0) and tt.min() >= -40 and tt.max() < 200   # sorted, inside the window
             assert np.all(a[p, n[p]:] == 0)
         assert abs(a[m.astype(bool)].mean() - 1 / (1 - 0.08)) < 0.1
+
+
+def test_usage_pattern_of_nsb_cluster_script():
+    """reference nsb_cluster_7.py:18-44: reads adc_count before the first event, calls next()
+    directly, does float arithmetic on the returned traces, reads toy.gain."""
+    toy = gen(n_pixels=21, nsb_rate=1.0, seed=3)
+    baseline = np.zeros(21)
+    baseline += np.mean(toy.adc_count, axis=-1)
+    assert not baseline.any()
+    for i in range(3):
+        toy.next()
+        trace = toy.adc_count
+        trace = trace - baseline
+        trace[trace < 0] = 0
+        trigger_trace = np.sum(trace, axis=0)
+        assert trigger_trace.shape == (50,) and trigger_trace.min() > 21 * 200
+    assert toy.gain.shape == (21,) and abs(toy.gain[0] - 5.8 / 2) < 1e-12 and toy.count == 2
