@@ -35,4 +35,25 @@ with open(os.path.join(out_dir, 'SUMMARY.md'), 'w') as f:
             ('%.3e (%d)' % (c['value'], c['cores'])) if c else '-', k.get('sm_mhz', '-'), ','.join(k.get('reasons', [])) or 'none'))
     f.write('\nncu summaries in this directory: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'ncu_*.txt')))) + '\n')
     f.write('\nLaunch lists: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'launches_*.csv')))) + '\n')
+import csv, collections
+lp = os.path.join(out_dir, 'launches_bench_default.csv')
+if os.path.exists(lp):
+    rows_ = list(csv.reader(open(lp)))
+    hi = next(i for i, r in enumerate(rows_) if r and r[0] == 'ID')
+    hdr = rows_[hi]; ix = {h: i for i, h in enumerate(hdr)}
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows_[hi + 1:]:
+        if len(r) < len(hdr):
+            continue
+        scale = {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}.get(r[ix['Metric Unit']], 1e-6)
+        a_ = agg[r[ix['Kernel Name']][:70]]
+        a_[0] += 1; a_[1] += float(r[ix['Metric Value']].replace(',', '')) * scale
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(out_dir, 'SUMMARY.md'), 'a') as f:
+        f.write('\n## ncu launch list of `python bench.py --no-cpu-baseline` (first 200 launches, `launches_bench_default.csv`)\n\n')
+        f.write('Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.  In the\n'
+                'CUDA-event timing of the same command K1 is 61.8 of 65.3 ms per step (94.6 %).\n\n')
+        f.write('| kernel | launches | total ms | share |\n|---|---|---|---|\n')
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write('| `%s` | %d | %.2f | %.1f %% |\n' % (k, v[0], v[1], 100 * v[1] / tot))
 print(open(os.path.join(out_dir, 'SUMMARY.md')).read())
