@@ -406,7 +406,7 @@ def test_usage_pattern_of_nsb_cluster_script():
     for i in range(3):
         toy.next()
         trace = toy.adc_count
-        trace = trace - baseline
+        trace = trace - baseline[:, None]     # (the script's own `trace - baseline[j]` does not broadcast)
         trace[trace < 0] = 0
         trigger_trace = np.sum(trace, axis=0)
         assert trigger_trace.shape == (50,) and trigger_trace.min() > 21 * 200
