@@ -310,14 +310,20 @@ def run_b200_arm(a):
     k_ms = sum(kernel_ms) / len(kernel_ms)
     algo_bytes = E * P * B * 2
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, sm_bound = None, None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(gen.kernel)
         if tj:
             traffic = tj['dram_bytes_per_sample'] * E * P * B
+            if a.workload == 'c4' and 'sm_issue_active_pct' in tj:
+                # the resources that actually bind this kernel, from the committed ncu capture
+                sm_bound = dict(issue_active_pct_of_peak=tj['sm_issue_active_pct'],
+                                shared_wavefronts_pct_of_peak=tj['shared_wavefronts_pct_of_peak'],
+                                active_threads_per_warp_inst=tj['active_threads_per_warp_inst'],
+                                source=tj.get('ncu'))
     roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=traffic, kernel='k_generate_' + gen.kernel, kernel_ms=k_ms,
+                    traffic=traffic, kernel='k_generate_' + gen.kernel, kernel_ms=k_ms, sm_bound=sm_bound,
                     algorithmic_bytes_per_launch=algo_bytes, peak_source=peak_src,
                     note='HBM-write roofline (2 B/sample). This workload is SM-issue-bound, not HBM-bound: '
                          '~245 photo-electron clusters per trace x 22 template taps; see DESIGN.md')
