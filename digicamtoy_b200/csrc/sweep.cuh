@@ -36,6 +36,16 @@ constexpr int SWEEP_MAX_BINS = 256;
 #ifndef DCT_SWEEP_HOIST_KEYS
 #define DCT_SWEEP_HOIST_KEYS 0
 #endif
+// cost-attribution experiments (profiles/r01/cost_attribution.txt); all produce WRONG cubes
+#ifndef DCT_EXP_NO_SLIDE
+#define DCT_EXP_NO_SLIDE 0
+#endif
+#ifndef DCT_EXP_NO_TAPS
+#define DCT_EXP_NO_TAPS 0
+#endif
+#ifndef DCT_EXP_CHEAP_RNG
+#define DCT_EXP_CHEAP_RNG 0
+#endif
 #ifndef DCT_SWEEP_MIN_BLOCKS
 #define DCT_SWEEP_MIN_BLOCKS 6
 #endif
@@ -128,7 +138,9 @@ k_generate_sweep(const GenArgs a) {
                 // slide by one cell: predicated, all lanes
                 const bool one = k >= 1;
                 if (one && (unsigned)kb < (unsigned)B) row[kb] = W[0];
+#if !DCT_EXP_NO_SLIDE
                 slide_window<TAPS>(W, one);
+#endif
                 if (k >= 2) {                                 // rare: gap longer than a cell
                     ++kb;
                     if (k > TAPS) {
@@ -156,6 +168,7 @@ k_generate_sweep(const GenArgs a) {
                 const unsigned act = __activemask();
                 const int j_lo = first_needed - __reduce_max_sync(act, cell);
                 const int j_hi = last_needed - __reduce_min_sync(act, cell);
+#if !DCT_EXP_NO_TAPS
 #pragma unroll
                 for (int g0 = 0; g0 < TAPS; g0 += SWEEP_GROUP) {
                     if (g0 + SWEEP_GROUP > j_lo && g0 < j_hi) {
@@ -171,6 +184,9 @@ k_generate_sweep(const GenArgs a) {
                         }
                     }
                 }
+#else
+                W[0] += A * u + (float)(j_lo + j_hi) + tlo[0].x + thi[0].x + uu.x + AA.y;   // keep the inputs alive
+#endif
             };
 #if DCT_SWEEP_HOIST_KEYS
             const PhiloxKeys ks = philox_keys(t.key.k0, t.key.k1);
@@ -178,7 +194,17 @@ k_generate_sweep(const GenArgs a) {
             ctr.y = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu); ctr.z = t.key.pixel; ctr.w = t.key.ev_lo;
             auto draw_nsb = [&](uint32_t i) { u32x4 c = ctr; c.x = i; return philox4x32_keyed(c, ks); };
 #else
+#if DCT_EXP_CHEAP_RNG
+            // COST-ATTRIBUTION EXPERIMENT ONLY (wrong statistics): a 4-multiply hash instead of Philox
+            auto draw_nsb = [&](uint32_t i) {
+                u32x4 c;
+                const uint32_t h = (i + 1u) * 0x9E3779B9u ^ t.key.pixel * 0x85EBCA6Bu ^ t.key.ev_lo * 0xC2B2AE35u;
+                c.x = h * 0xD2511F53u; c.y = (h ^ (h >> 15)) * 0xCD9E8D57u; c.z = (h ^ (h >> 13)) * 0x27D4EB2Fu; c.w = (h ^ (h >> 16)) * 0x165667B1u;
+                return c;
+            };
+#else
             auto draw_nsb = [&](uint32_t i) { return draw_block(t.key, STREAM_NSB, i); };
+#endif
 #endif
 #if DCT_SWEEP_UNROLL2
             // two photo-electrons per iteration: their Philox blocks and samplers are independent
