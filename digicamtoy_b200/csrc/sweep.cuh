@@ -9,9 +9,10 @@
 //
 // Divergence control (ncu, profiles/r01): the one-cell slide is a predicated select executed by
 // every lane every iteration (22 FSEL) instead of a branchy loop that ran with 7 of 32 lanes; only
-// gaps longer than one cell (0.5 % of pe at 1 GHz) take the loop.  Taps that can only land in
-// dropped or non-existent bins for every lane of the warp are skipped in groups of four using the
-// warp-wide min / max of the cell index (REDUX).
+// gaps longer than one cell (0.5 % of pe at 1 GHz) take the loop.  Optional (DCT_SWEEP_SKIP=1, off):
+// taps that can only land in dropped or non-existent bins for every lane of the warp are skipped
+// in groups of four using the warp-wide min / max of the cell index (REDUX) -- a win with scalar
+// FFMA taps, a loss once the taps became FFMA2 (DESIGN.md tuning record).
 //
 // It consumes the same Philox blocks and performs the same floating-point operations per kept bin,
 // in the same order, as k_generate_scatter: both kernels produce identical cubes (tests check it).
@@ -46,8 +47,11 @@ constexpr int SWEEP_MAX_BINS = 256;
 #ifndef DCT_EXP_CHEAP_RNG
 #define DCT_EXP_CHEAP_RNG 0
 #endif
+#ifndef DCT_SWEEP_SKIP
+#define DCT_SWEEP_SKIP 0      // 1: skip tap groups no lane of the warp needs (REDUX min / max of the cell); measured slower once the taps became FFMA2
+#endif
 #ifndef DCT_SWEEP_MIN_BLOCKS
-#define DCT_SWEEP_MIN_BLOCKS 6
+#define DCT_SWEEP_MIN_BLOCKS 5
 #endif
 constexpr int SWEEP_GROUP = DCT_SWEEP_GROUP;   // taps per skip group (even)
 constexpr double SWEEP_MIN_MEAN_PE = 0.0;    // measured (scripts/kernel_crossover.py): sweep >= scatter at every rate, 0.7 .. 240 pe / trace
@@ -165,9 +169,13 @@ k_generate_sweep(const GenArgs a) {
                 const float4* thi = tab_hi + f;
                 const float2 uu = make_float2(u, u), AA = make_float2(A, A);
                 // warp-uniform tap range: skip groups no lane needs
+#if DCT_SWEEP_SKIP
                 const unsigned act = __activemask();
                 const int j_lo = first_needed - __reduce_max_sync(act, cell);
                 const int j_hi = last_needed - __reduce_min_sync(act, cell);
+#else
+                const int j_lo = 0, j_hi = TAPS;
+#endif
 #if !DCT_EXP_NO_TAPS
 #pragma unroll
                 for (int g0 = 0; g0 < TAPS; g0 += SWEEP_GROUP) {
