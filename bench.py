@@ -315,7 +315,8 @@ def run_b200_arm(a):
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(gen.kernel)
         if tj:
-            traffic = tj['dram_bytes_per_sample'] * E * P * B
+            per_sample = tj.get(a.workload, tj)['dram_bytes_per_sample'] if a.workload != 'c4' else tj['dram_bytes_per_sample']
+            traffic = per_sample * E * P * B
             if a.workload == 'c4' and 'sm_issue_active_pct' in tj:
                 # the resources that actually bind this kernel, from the committed ncu capture
                 sm_bound = dict(issue_active_pct_of_peak=tj['sm_issue_active_pct'],
