@@ -169,10 +169,14 @@ k_generate_sweep(const GenArgs a) {
                 const float4* thi = tab_hi + f;
                 const float2 uu = make_float2(u, u), AA = make_float2(A, A);
                 // warp-uniform tap range: skip groups no lane needs
-#if DCT_SWEEP_SKIP
+#if DCT_SWEEP_SKIP == 1
                 const unsigned act = __activemask();
                 const int j_lo = first_needed - __reduce_max_sync(act, cell);
                 const int j_hi = last_needed - __reduce_min_sync(act, cell);
+#elif DCT_SWEEP_SKIP == 2
+                // only the end of the trace (where most of the unneeded taps are): one REDUX
+                const int j_lo = 0;
+                const int j_hi = last_needed - __reduce_min_sync(__activemask(), cell);
 #else
                 const int j_lo = 0, j_hi = TAPS;
 #endif
