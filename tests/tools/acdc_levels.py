@@ -1,7 +1,7 @@
 """Throughput of every (NSB, n_photon) level of config_files/ac_dc.yml and of dark.yml on the GPU,
 next to the CPU oracle on one core (the table BASELINE.md gives for the reference).  GPU + CPU."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from digicamtoy_b200 import NTraceGenerator, workloads
 from oracle import reference_port as orc

@@ -3,7 +3,7 @@ against the closed form (oracle.closed_form_moments).  Statistical error on a bi
 so systematic deviations of the GPU samplers at the 1e-3 LSB level would show.  GPU only; uses the
 oracle as the checker (test infrastructure)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from digicamtoy_b200 import NTraceGenerator, workloads
 from digicamtoy_b200.stats import CubeStats
