@@ -20,6 +20,10 @@
 #include "selftest.cuh"
 #include "dump.cuh"
 
+#ifndef DCT_STATS_TILE_MAX_BINS
+#define DCT_STATS_TILE_MAX_BINS 64      // longer traces use the warp-per-trace statistics kernel
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -534,7 +538,7 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
         int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
         charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));
-        if (a.B > 64) {
+        if (a.B > DCT_STATS_TILE_MAX_BINS) {
             // long traces: warp-per-trace variant (see stats.cuh)
             const size_t smem = ((size_t)n_hist + dct::STATS_CHARGE_WIN +
                                  (size_t)dct::STATS_FAST_WARPS * dct::STATS_WIN * 16) * sizeof(unsigned int);
@@ -551,7 +555,7 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         }
         const size_t tile_words = ((size_t)dct::STATS_ROWS * wpr + 3) & ~(size_t)3;
         const size_t smem = (2 * tile_words + (size_t)n_hist + dct::STATS_CHARGE_WIN +
-                             (size_t)(dct::STATS_ROWS / 32) * dct::STATS_WIN * 16) * sizeof(unsigned int);
+                             (size_t)dct::STATS_PRIV_WORDS) * sizeof(unsigned int);
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(dct::k_stats_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));

@@ -126,6 +126,10 @@ k_stats(const StatsArgs a) {
 constexpr int STATS_WIN = 64;
 constexpr int STATS_ROWS = 128;               // traces per tile = threads per CTA
 constexpr int STATS_CHARGE_WIN = 1024;        // CTA-private window of the charge histogram
+constexpr int STATS_PRIV_COLS = (STATS_ROWS / 32) * STATS_WIN;                 // (warp, value) columns
+constexpr int STATS_PRIV_WORDS = STATS_PRIV_COLS * 16;                         // 32-bit words of the columns
+// (two independent column sets -- one per half-word -- were measured: the shorter dependency chain
+//  did not pay for the occupancy lost to the extra 16 KB: 3.2 ms instead of 2.4 ms per C4 cube)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -151,7 +155,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;      // my column: priv[w * 32]
-    for (int i = tid; i < n_hist + STATS_CHARGE_WIN + (STATS_ROWS / 32) * STATS_WIN * 16; i += STATS_ROWS)
+    for (int i = tid; i < n_hist + STATS_CHARGE_WIN + STATS_PRIV_WORDS; i += STATS_ROWS)
         hist_s[i] = 0u;
     __syncthreads();
 
@@ -163,6 +167,9 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     long long bs[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};       // bins 2*lane, 2*lane+1, 2*(lane+32), +1
     const unsigned int hist_addr = (unsigned int)__cvta_generic_to_shared(hist_s) - 4u * (unsigned int)a.adc_min;
     int my_samples = 0;
+    // Every clamped charge would hit the same end bin of the global histogram: count those in
+    // registers (ablation, profiles/r01/cost_attribution.txt: as atomics they cost 2.5 ms of 3.8).
+    unsigned int n_charge_over = 0, n_charge_under = 0;
 
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pb = (int)(item % (uint64_t)n_pb);
@@ -195,8 +202,6 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             const unsigned int* row = cur + tid * wpr;
             int ts = 0;
             unsigned int tq = 0;
-            int cs[4] = {0, 0, 0, 0};                            // this event's column sums (one word per slot)
-            unsigned int cq[4] = {0u, 0u, 0u, 0u};
             for (int w = 0; w < wpr; ++w) {
                 const unsigned int word = mine ? row[w] : 0u;
                 const int v0 = (int)(short)word, v1 = (int)word >> 16;
@@ -208,26 +213,36 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                     if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v0);
                     if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v1);
                 }
-                if (a.bin_sum) {
-                    // column sums over the warp's 32 rows; lane (w % 32) keeps the bins of word w
-                    const int s0 = __reduce_add_sync(0xffffffffu, v0), s1 = __reduce_add_sync(0xffffffffu, v1);
-                    const unsigned int r0 = __reduce_add_sync(0xffffffffu, q0), r1 = __reduce_add_sync(0xffffffffu, q1);
-                    if (lane == (w & 31)) {
-                        if (w < 32) { cs[0] = s0; cs[1] = s1; cq[0] = r0; cq[1] = r1; }
-                        else        { cs[2] = s0; cs[3] = s1; cq[2] = r0; cq[3] = r1; }
+            }
+            if (a.bin_sum) {
+                // column sums: lane = word column, this warp's 32 rows of the tile (consecutive lanes read
+                // consecutive words: conflict-free); replaces 4 REDUX per word (~38 cycles each)
+                const int r_end = min(np, 32 * (wib + 1));
+                for (int slot = 0; slot < 2; ++slot) {
+                    const int w = lane + 32 * slot;
+                    if (w < wpr) {
+                        int s0 = 0, s1 = 0;
+                        unsigned int r0 = 0u, r1 = 0u;
+                        for (int r = 32 * wib; r < r_end; ++r) {
+                            const unsigned int word = cur[r * wpr + w];
+                            const int v0 = (int)(short)word, v1 = (int)word >> 16;
+                            s0 += v0; s1 += v1;
+                            r0 += (unsigned int)(v0 * v0); r1 += (unsigned int)(v1 * v1);
+                        }
+                        bs[2 * slot] += s0; bs[2 * slot + 1] += s1;
+                        bq[2 * slot] += r0; bq[2 * slot + 1] += r1;
                     }
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { bs[r] += cs[r]; bq[r] += cq[r]; }
             if (mine) {
                 pix_s += ts;
                 pix_q += tq;
                 if (a.charge_hist) {
-                    long long bin = (long long)ts - charge_ref - a.charge_lo;
-                    bin = bin < 0 ? 0 : (bin >= a.n_charge_bins ? a.n_charge_bins - 1 : bin);
+                    const long long bin = (long long)ts - charge_ref - a.charge_lo;
                     const long long cw = bin - charge_win_lo;
                     if (cw >= 0 && cw < STATS_CHARGE_WIN) atomicAdd(&charge_s[cw], 1u);
+                    else if (bin >= a.n_charge_bins - 1) ++n_charge_over;
+                    else if (bin <= 0) ++n_charge_under;
                     else atomicAdd(a.charge_hist + bin, 1ull);
                 }
             }
@@ -249,6 +264,12 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             if (a.pixel_sumsq) atomicAdd(a.pixel_sumsq + pixel, (double)pix_q);
         }
     }
+    if (a.charge_hist) {
+        n_charge_over = __reduce_add_sync(0xffffffffu, n_charge_over);
+        n_charge_under = __reduce_add_sync(0xffffffffu, n_charge_under);
+        if (lane == 0 && n_charge_over) atomicAdd(a.charge_hist + (a.n_charge_bins - 1), (unsigned long long)n_charge_over);
+        if (lane == 0 && n_charge_under) atomicAdd(a.charge_hist, (unsigned long long)n_charge_under);
+    }
     const int bins[4] = {2 * lane, 2 * lane + 1, 2 * (lane + 32), 2 * (lane + 32) + 1};
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -259,7 +280,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     __syncthreads();
     if (a.adc_hist) {
         // fold every thread-private column into the CTA histogram
-        for (int i = tid; i < (STATS_ROWS / 32) * STATS_WIN; i += STATS_ROWS) {
+        for (int i = tid; i < STATS_PRIV_COLS; i += STATS_ROWS) {
             const unsigned short* col = priv_all + (size_t)i * 32;
             unsigned int c = 0;
             for (int l = 0; l < 32; ++l) c += col[(l + tid) & 31];
