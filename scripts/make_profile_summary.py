@@ -52,7 +52,7 @@ if os.path.exists(lp):
     with open(os.path.join(out_dir, 'SUMMARY.md'), 'a') as f:
         f.write('\n## ncu launch list of `python bench.py --no-cpu-baseline` (first 200 launches, `launches_bench_default.csv`)\n\n')
         f.write('Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.  In the\n'
-                'CUDA-event timing of the same command K1 is 61.8 of 65.3 ms per step (94.6 %).\n\n')
+                'CUDA-event timing of the same command K1 is 59.8 of 62.2 ms per step (96 %).\n\n')
         f.write('| kernel | launches | total ms | share |\n|---|---|---|---|\n')
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %d | %.2f | %.1f %% |\n' % (k, v[0], v[1], 100 * v[1] / tot))
