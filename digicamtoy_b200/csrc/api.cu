@@ -20,8 +20,16 @@
 #include "selftest.cuh"
 #include "dump.cuh"
 
-#ifndef DCT_STATS_TILE_MAX_BINS
-#define DCT_STATS_TILE_MAX_BINS 64      // longer traces use the warp-per-trace statistics kernel
+#ifndef DCT_STATS_COMPACT_BINS
+#define DCT_STATS_COMPACT_BINS 0        // above this trace length the tile kernel runs in its compact layout
+                                        // (measured: 3.36 against 5.71 ms on the 92-bin dark cube, where the other
+                                        //  layout leaves 2 CTAs per SM; 2.19 against 2.54 ms on the 50-bin C4 cube)
+#endif
+#ifndef DCT_STATS_COMPACT_HIST
+#define DCT_STATS_COMPACT_HIST 1024     // ... with a CTA histogram of this many ADC values
+#endif
+#ifndef DCT_STATS_COMPACT_SINGLE
+#define DCT_STATS_COMPACT_SINGLE 1      // ... and one tile buffer
 #endif
 
 namespace {
@@ -538,23 +546,19 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
         int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
         charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));
-        if (a.B > DCT_STATS_TILE_MAX_BINS) {
-            // long traces: warp-per-trace variant (see stats.cuh)
-            const size_t smem = ((size_t)n_hist + dct::STATS_CHARGE_WIN +
-                                 (size_t)dct::STATS_FAST_WARPS * dct::STATS_WIN * 16) * sizeof(unsigned int);
-            if (smem > 48 * 1024)
-                CK(cudaFuncSetAttribute(dct::k_stats_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint64_t blocks = (uint64_t)h->sm_count * 3;
-            const uint64_t n_warps = blocks * dct::STATS_FAST_WARPS;
-            uint64_t n_slices = (4 * n_warps + a.P - 1) / a.P;
-            n_slices = std::max<uint64_t>(1, std::min<uint64_t>(n_slices, n_events));
-            dct::k_stats_warp<<<(unsigned)blocks, dct::STATS_FAST_WARPS * 32, smem, (cudaStream_t)stream>>>(
-                a, win_lo, (int)n_slices, charge_win_lo);
-            CK(cudaGetLastError());
-            return DCT_OK;
+        // Long traces: the two tile buffers plus a full-range CTA histogram would leave two CTAs per
+        // SM.  Compact layout: one tile buffer, CTA histogram over a window around the pedestal
+        // (samples beyond it go to the global histogram one atomic each: bright pulses only).
+        const bool compact = a.B > DCT_STATS_COMPACT_BINS && n_hist > DCT_STATS_COMPACT_HIST;
+        const int single_tile = compact ? DCT_STATS_COMPACT_SINGLE : 0;
+        const int n_hist_s = compact ? DCT_STATS_COMPACT_HIST : n_hist;
+        int hist_lo = a.adc_min;
+        if (compact) {
+            hist_lo = win_lo - DCT_STATS_COMPACT_HIST / 8;
+            hist_lo = std::max(a.adc_min, std::min(hist_lo, a.adc_max + 1 - n_hist_s));
         }
         const size_t tile_words = ((size_t)dct::STATS_ROWS * wpr + 3) & ~(size_t)3;
-        const size_t smem = (2 * tile_words + (size_t)n_hist + dct::STATS_CHARGE_WIN +
+        const size_t smem = ((single_tile ? 1 : 2) * tile_words + (size_t)n_hist_s + dct::STATS_CHARGE_WIN +
                              (size_t)dct::STATS_PRIV_WORDS) * sizeof(unsigned int);
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(dct::k_stats_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,7 +570,7 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         n_slices = std::max<uint64_t>(1, std::min<uint64_t>(n_slices, n_events));
         blocks = std::min<uint64_t>(blocks, n_pb * n_slices);
         dct::k_stats_tile<<<(unsigned)blocks, dct::STATS_ROWS, smem, (cudaStream_t)stream>>>(
-            a, win_lo, (int)n_slices, charge_win_lo);
+            a, win_lo, (int)n_slices, charge_win_lo, hist_lo, n_hist_s, single_tile);
         CK(cudaGetLastError());
         return DCT_OK;
     }

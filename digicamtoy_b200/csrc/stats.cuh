@@ -142,20 +142,41 @@ __device__ __forceinline__ void red_shared_inc(unsigned int smem_addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_addr) : "memory");
 }
 
+// Samples beyond the CTA histogram's slice (compact layout only, bright pulses only).  Out of line and
+// with its accumulators in local memory: the per-sample loop must not pay registers for it.
+struct HistOutside {
+    double m[4];                    // power sums of those samples
+    unsigned int rail_hi, rail_lo;  // those at adc_max / adc_min: one global address each, so counted here
+};
+__device__ __noinline__ void hist_outside(HistOutside& o, unsigned long long* adc_hist, int adc_min, int adc_max,
+                                          int v, unsigned int c, bool defer_rails) {
+    if (defer_rails && v == adc_max) { o.rail_hi += c; return; }
+    if (defer_rails && v == adc_min) { o.rail_lo += c; return; }
+    const unsigned int hg = (unsigned int)(v - adc_min);
+    if (hg <= (unsigned int)(adc_max - adc_min)) atomicAdd(adc_hist + hg, (unsigned long long)c);
+    const double x = (double)v, cd = (double)c;
+    o.m[0] += cd * x; o.m[1] += cd * x * x; o.m[2] += cd * x * x * x; o.m[3] += cd * x * x * x * x;
+}
+
 __global__ void __launch_bounds__(STATS_ROWS)
-k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
+k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
+             int hist_lo, int n_hist_s, int single_tile) {
+    // hist_lo / n_hist_s: the slice [hist_lo, hist_lo + n_hist_s) of the ADC range that the CTA
+    // histogram covers (the whole range for short traces; for long ones a window, so that more CTAs
+    // fit on an SM -- samples outside it go straight to the global histogram).  single_tile: one
+    // tile buffer instead of two, the other resident CTAs hide the load.
     extern __shared__ __align__(16) unsigned int smem_u[];
     const int n_hist = a.adc_max - a.adc_min + 1;
     const int wpr = a.B >> 1;                                   // 32-bit words per trace
     const int tile_words = (STATS_ROWS * wpr + 3) & ~3;
     unsigned int* tile0 = smem_u;
-    unsigned int* tile1 = smem_u + tile_words;
-    unsigned int* hist_s = tile1 + tile_words;                  // [n_hist]
-    unsigned int* charge_s = hist_s + n_hist;                   // [STATS_CHARGE_WIN]
+    unsigned int* tile1 = single_tile ? tile0 : smem_u + tile_words;
+    unsigned int* hist_s = tile1 + tile_words;                  // [n_hist_s]
+    unsigned int* charge_s = hist_s + n_hist_s;                 // [STATS_CHARGE_WIN]
     unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;      // my column: priv[w * 32]
-    for (int i = tid; i < n_hist + STATS_CHARGE_WIN + STATS_PRIV_WORDS; i += STATS_ROWS)
+    for (int i = tid; i < n_hist_s + STATS_CHARGE_WIN + STATS_PRIV_WORDS; i += STATS_ROWS)
         hist_s[i] = 0u;
     __syncthreads();
 
@@ -165,7 +186,22 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     const uint64_t event_words = (uint64_t)a.P * wpr;
     const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
     long long bs[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};       // bins 2*lane, 2*lane+1, 2*(lane+32), +1
-    const unsigned int hist_addr = (unsigned int)__cvta_generic_to_shared(hist_s) - 4u * (unsigned int)a.adc_min;
+    const unsigned int hist_addr = (unsigned int)__cvta_generic_to_shared(hist_s);
+    HistOutside outside = {{0, 0, 0, 0}, 0u, 0u};
+    // a sample outside the thread-private window: CTA histogram, or the global one beyond its slice
+    // (beyond the slice the per-sample loop only raises a flag; the trace is then scanned a second
+    //  time for those samples -- a call in the per-sample loop cost 10% even when never taken)
+    bool beyond = false;
+    auto hist_rare = [&](int v) {
+        const unsigned int hs = (unsigned int)(v - hist_lo);
+        if (hs < (unsigned int)n_hist_s) red_shared_inc(hist_addr + 4u * hs);
+        else beyond = true;
+    };
+    auto hist_add = [&](int v, unsigned int c) {                 // c samples of value v (fold of the columns)
+        const unsigned int hs = (unsigned int)(v - hist_lo);
+        if (hs < (unsigned int)n_hist_s) atomicAdd(&hist_s[hs], c);
+        else hist_outside(outside, a.adc_hist, a.adc_min, a.adc_max, v, c, false);
+    };
     int my_samples = 0;
     // Every clamped charge would hit the same end bin of the global histogram: count those in
     // registers (ablation, profiles/r01/cost_attribution.txt: as atomics they cost 2.5 ms of 3.8).
@@ -194,7 +230,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             unsigned int* nxt = ((e - e_begin) & 1) ? tile0 : tile1;
             cp_async_wait_all();
             __syncthreads();                                     // tile e landed; tile e-1 fully consumed
-            if (e + 1 < e_end) {
+            if (!single_tile && e + 1 < e_end) {
                 const uint32_t* src = src0 + (e + 1) * event_words;
                 for (int v = tid; v < n_vec; v += STATS_ROWS) cp_async16(nxt + 4 * v, src + 4 * v);
                 cp_async_commit();
@@ -210,9 +246,20 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                 tq += q0 + q1;
                 if (a.adc_hist && mine) {
                     const unsigned h0 = (unsigned)(v0 - win_lo), h1 = (unsigned)(v1 - win_lo);
-                    if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v0);
-                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else red_shared_inc(hist_addr + 4u * (unsigned int)v1);
+                    if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else hist_rare(v0);
+                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else hist_rare(v1);
                 }
+            }
+            if (beyond) {                                        // compact layout, bright traces only
+                for (int w = 0; w < wpr; ++w) {
+                    const unsigned int word = row[w];
+                    const int v[2] = {(int)(short)word, (int)word >> 16};
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if ((unsigned)(v[k] - win_lo) >= (unsigned)STATS_WIN && (unsigned)(v[k] - hist_lo) >= (unsigned)n_hist_s)
+                            hist_outside(outside, a.adc_hist, a.adc_min, a.adc_max, v[k], 1u, true);
+                }
+                beyond = false;
             }
             if (a.bin_sum) {
                 // column sums: lane = word column, this warp's 32 rows of the tile (consecutive lanes read
@@ -234,6 +281,12 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                     }
                 }
             }
+            if (single_tile && e + 1 < e_end) {
+                __syncthreads();                                 // every row and column of the tile was read
+                const uint32_t* src = src0 + (e + 1) * event_words;
+                for (int v = tid; v < n_vec; v += STATS_ROWS) cp_async16(tile0 + 4 * v, src + 4 * v);
+                cp_async_commit();
+            }
             if (mine) {
                 pix_s += ts;
                 pix_q += tq;
@@ -252,8 +305,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
                 for (int w = 0; w < STATS_WIN; ++w) {
                     const unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)priv[w * 32]);
                     priv[w * 32] = 0;
-                    const int v = win_lo + w - a.adc_min;
-                    if (lane == 0 && c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+                    if (lane == 0 && c) hist_add(win_lo + w, c);
                 }
                 my_samples = 0;
             }
@@ -284,8 +336,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             const unsigned short* col = priv_all + (size_t)i * 32;
             unsigned int c = 0;
             for (int l = 0; l < 32; ++l) c += col[(l + tid) & 31];
-            const int v = win_lo + (i % STATS_WIN) - a.adc_min;
-            if (c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
+            if (c) hist_add(win_lo + (i % STATS_WIN), c);
         }
         __syncthreads();
     }
@@ -295,13 +346,20 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
             if (c && charge_win_lo + i < a.n_charge_bins) atomicAdd(a.charge_hist + charge_win_lo + i, (unsigned long long)c);
         }
     // flush the CTA histogram; the raw power sums come from it (exact: integers < 2^53 per CTA)
-    double m[4] = {0, 0, 0, 0};
+    if (a.adc_hist) {                                            // rails seen beyond the slice
+        const unsigned int hi = __reduce_add_sync(0xffffffffu, outside.rail_hi);
+        const unsigned int lo = __reduce_add_sync(0xffffffffu, outside.rail_lo);
+        if (lane == 0 && hi) hist_outside(outside, a.adc_hist, a.adc_min, a.adc_max, a.adc_max, hi, false);
+        if (lane == 0 && lo) hist_outside(outside, a.adc_hist, a.adc_min, a.adc_max, a.adc_min, lo, false);
+    }
+    double m[4] = {outside.m[0], outside.m[1], outside.m[2], outside.m[3]};
     if (a.adc_hist) {
-        for (int i = tid; i < n_hist; i += STATS_ROWS) {
+        for (int i = tid; i < n_hist_s; i += STATS_ROWS) {
             const unsigned int c = hist_s[i];
-            if (c) {
-                atomicAdd(a.adc_hist + i, (unsigned long long)c);
-                const double x = (double)(i + a.adc_min), cd = (double)c;
+            const int g = i + hist_lo - a.adc_min;
+            if (c && g >= 0 && g < n_hist) {
+                atomicAdd(a.adc_hist + g, (unsigned long long)c);
+                const double x = (double)(i + hist_lo), cd = (double)c;
                 m[0] += cd * x; m[1] += cd * x * x; m[2] += cd * x * x * x; m[3] += cd * x * x * x * x;
             }
         }
@@ -315,199 +373,9 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
     }
 }
 
-// ---- warp-per-trace variant (v3), kept for long traces (B > 64) where the tile kernel's
-// shared-memory footprint leaves too few warps per SM (dark.yml: 5.7 ms vs 8.5 ms per 16384 events)
-constexpr int STATS_FAST_WARPS = 8;
-constexpr int STATS_FLUSH_TRACES = 8192;      // 4 samples per lane per trace: 16-bit counters stay < 2^15
-
-struct StatsLane {
-    long long bs[4], bq[4];          // per-bin sums, flushed from the 32-bit accumulators below
-    int bs32[4];
-    unsigned int bq32[4];
-};
-
-// Two samples of one 32-bit word.  Integer only: 1 add + 2 multiply-adds per sample for the sums, a
-// plain 16-bit read-modify-write of the lane-private histogram column.
-__device__ __forceinline__ void stats_word(const StatsArgs& a, uint32_t word, int slot, unsigned short* priv,
-                                           unsigned int* hist_s, int win_lo, StatsLane& L, int& ts,
-                                           unsigned int& pq32) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int v = h ? ((int)word >> 16) : (int)(short)word;
-        L.bs32[slot + h] += v;
-        L.bq32[slot + h] += (unsigned int)(v * v);
-        pq32 += (unsigned int)(v * v);
-        ts += v;
-        if (a.adc_hist) {
-            const unsigned w = (unsigned)(v - win_lo);
-            if (w < (unsigned)STATS_WIN) priv[w * 32] += 1;
-            else atomicAdd(&hist_s[v - a.adc_min], 1u);
-        }
-    }
-}
-
-__device__ __forceinline__ void stats_fold_private(unsigned short* priv_all, unsigned int* hist_s, int win_lo,
-                                                   int adc_min, int n_hist) {
-    // all warps of the CTA: fold every lane-private column into the CTA histogram and clear it
-    for (int i = threadIdx.x; i < STATS_FAST_WARPS * STATS_WIN; i += blockDim.x) {
-        unsigned short* col = priv_all + (size_t)i * 32;
-        unsigned int c = 0;
-        for (int l = 0; l < 32; ++l) {
-            const int k = (l + threadIdx.x) & 31;
-            c += col[k];
-            col[k] = 0;
-        }
-        const int v = win_lo + (i % STATS_WIN) - adc_min;
-        if (c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
-    }
-}
-
-constexpr int STATS_T = 8;                    // traces per pipeline stage
-// (window sizes shared with the tile kernel)
-//      // CTA-private window of the charge histogram
-
-// Work item = (pixel, slice of events): a warp walks the traces of ONE pixel, so the per-pixel sums
-// stay in registers and are flushed with two atomics per item (the first version issued three
-// global atomics per trace onto a few hundred hot addresses and was bound by L2 atomic
-// serialisation: 8-11 ms per 2 GB cube instead of ~1 ms).
-__global__ void __launch_bounds__(STATS_FAST_WARPS * 32, 3)
-k_stats_warp(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo) {
-    extern __shared__ unsigned int smem_u[];
-    const int n_hist = a.adc_max - a.adc_min + 1;
-    unsigned int* hist_s = smem_u;                                               // [n_hist]
-    unsigned int* charge_s = smem_u + n_hist;                                    // [STATS_CHARGE_WIN]
-    unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;
-    for (int i = threadIdx.x; i < n_hist + STATS_CHARGE_WIN + STATS_FAST_WARPS * STATS_WIN * 16; i += blockDim.x)
-        smem_u[i] = 0u;
-    __syncthreads();
-
-    const uint64_t warp = (uint64_t)blockIdx.x * STATS_FAST_WARPS + wib;
-    const uint64_t n_warps = (uint64_t)gridDim.x * STATS_FAST_WARPS;
-    const int wpr = a.B >> 1;                                                    // 32-bit words per trace
-    const bool has0 = lane < wpr, has1 = lane + 32 < wpr;
-    StatsLane L;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { L.bs[r] = 0; L.bq[r] = 0; L.bs32[r] = 0; L.bq32[r] = 0u; }
-    const uint32_t* cube = reinterpret_cast<const uint32_t*>(a.adc);
-    const uint64_t n_events = a.n_traces / (uint64_t)a.P;
-    const uint64_t n_items = (uint64_t)a.P * n_slices;
-    const uint64_t row_words = (uint64_t)a.P * wpr;                              // words between events
-    int lane_samples = 0;                                                        // bound on a private counter
-
-    for (uint64_t item = warp; item < n_items; item += n_warps) {
-        const int pixel = (int)(item % (uint64_t)a.P);
-        const uint64_t slice = item / (uint64_t)a.P;
-        const uint64_t e_begin = slice * n_events / n_slices, e_end = (slice + 1) * n_events / n_slices;
-        const long long charge_ref = (long long)a.B * llrintf(a.baseline[pixel]);
-        long long pix_s = 0;
-        double pix_q = 0.0;
-        const uint32_t* base = cube + (uint64_t)pixel * wpr;
-        // software pipeline: the words of the next STATS_T traces are in flight while the current
-        // ones are processed (the first version was latency-bound: ~13 KB in flight per SM)
-        uint32_t w0[STATS_T], w1[STATS_T], n0[STATS_T], n1[STATS_T];
-#pragma unroll
-        for (int tr = 0; tr < STATS_T; ++tr) {
-            const bool ok = e_begin + tr < e_end;
-            const uint32_t* row = base + (e_begin + tr) * row_words;
-            w0[tr] = (ok && has0) ? __ldcs(row + lane) : 0u;
-            w1[tr] = (ok && has1) ? __ldcs(row + lane + 32) : 0u;
-        }
-        for (uint64_t e = e_begin; e < e_end; e += STATS_T) {
-#pragma unroll
-            for (int tr = 0; tr < STATS_T; ++tr) {
-                const bool ok = e + STATS_T + tr < e_end;
-                const uint32_t* row = base + (e + STATS_T + tr) * row_words;
-                n0[tr] = (ok && has0) ? __ldcs(row + lane) : 0u;
-                n1[tr] = (ok && has1) ? __ldcs(row + lane + 32) : 0u;
-            }
-            unsigned int pq32 = 0u;
-#pragma unroll
-            for (int tr = 0; tr < STATS_T; ++tr) {
-                if (e + tr >= e_end) continue;
-                int ts = 0;
-                if (has0) stats_word(a, w0[tr], 0, priv, hist_s, win_lo, L, ts, pq32);
-                if (has1) stats_word(a, w1[tr], 2, priv, hist_s, win_lo, L, ts, pq32);
-                if (a.pixel_sum || a.charge_hist) {
-                    ts = __reduce_add_sync(0xffffffffu, ts);
-                    pix_s += ts;
-                    if (a.charge_hist && lane == 0) {
-                        long long bin = (long long)ts - charge_ref - a.charge_lo;
-                        bin = bin < 0 ? 0 : (bin >= a.n_charge_bins ? a.n_charge_bins - 1 : bin);
-                        const long long w = bin - charge_win_lo;
-                        if (w >= 0 && w < STATS_CHARGE_WIN) atomicAdd(&charge_s[w], 1u);
-                        else atomicAdd(a.charge_hist + bin, 1ull);
-                    }
-                }
-            }
-            // widen the 32-bit accumulators (8 traces x 4 samples x v^2 < 2^32 for |v| <= 11585)
-            pix_q += (double)pq32;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                L.bs[r] += L.bs32[r]; L.bq[r] += L.bq32[r];
-                L.bs32[r] = 0; L.bq32[r] = 0u;
-            }
-#pragma unroll
-            for (int tr = 0; tr < STATS_T; ++tr) { w0[tr] = n0[tr]; w1[tr] = n1[tr]; }
-            lane_samples += 4 * STATS_T;
-            if (a.adc_hist && lane_samples >= 60000) {                           // warp-private: fold my columns
-                __syncwarp();
-                for (int w = 0; w < STATS_WIN; ++w) {
-                    const unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)priv[w * 32]);
-                    priv[w * 32] = 0;
-                    const int v = win_lo + w - a.adc_min;
-                    if (lane == 0 && c && v >= 0 && v < n_hist) atomicAdd(&hist_s[v], c);
-                }
-                lane_samples = 0;
-            }
-        }
-        if (a.pixel_sum) {
-            pix_q = warp_sum(pix_q);
-            if (lane == 0) {
-                atomicAdd(a.pixel_sum + pixel, (double)pix_s);
-                if (a.pixel_sumsq) atomicAdd(a.pixel_sumsq + pixel, pix_q);
-            }
-        }
-    }
-    // lane owns bins 2*lane, 2*lane+1 (first word) and 2*(lane+32), 2*(lane+32)+1 (second word)
-    const int bins[4] = {2 * lane, 2 * lane + 1, 2 * (lane + 32), 2 * (lane + 32) + 1};
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-        if (bins[r] < a.B) {
-            if (a.bin_sum) atomicAdd(a.bin_sum + bins[r], (double)L.bs[r]);
-            if (a.bin_sumsq) atomicAdd(a.bin_sumsq + bins[r], (double)L.bq[r]);
-        }
-    __syncthreads();
-    if (a.adc_hist) {
-        stats_fold_private(priv_all, hist_s, win_lo, a.adc_min, n_hist);
-        __syncthreads();
-    }
-    if (a.charge_hist)
-        for (int i = threadIdx.x; i < STATS_CHARGE_WIN; i += blockDim.x) {
-            const unsigned int c = charge_s[i];
-            if (c && charge_win_lo + i < a.n_charge_bins) atomicAdd(a.charge_hist + charge_win_lo + i, (unsigned long long)c);
-        }
-    // flush the CTA histogram; the raw power sums come from it (exact: integers < 2^53 per CTA)
-    double m[4] = {0, 0, 0, 0};
-    if (a.adc_hist) {
-        for (int i = threadIdx.x; i < n_hist; i += blockDim.x) {
-            const unsigned int c = hist_s[i];
-            if (c) {
-                atomicAdd(a.adc_hist + i, (unsigned long long)c);
-                const double x = (double)(i + a.adc_min), cd = (double)c;
-                m[0] += cd * x; m[1] += cd * x * x; m[2] += cd * x * x * x; m[3] += cd * x * x * x * x;
-            }
-        }
-    }
-    if (a.moments && a.adc_hist) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double v = warp_sum(m[k]);
-            if (lane == 0 && v != 0.0) atomicAdd(a.moments + k, v);
-        }
-    }
-}
+// (A warp-per-trace variant served traces longer than 64 bins until the compact layout above made the
+//  tile kernel faster there too: 3.4 against 5.7 ms per 16384-event dark.yml cube,
+//  profiles/r01/k3_compact_variants.txt.  It is in the history, not in the build.)
 
 // K0: nothing but the stores K1 issues.  16 bytes per thread per iteration, grid-stride.
 __global__ void __launch_bounds__(256)

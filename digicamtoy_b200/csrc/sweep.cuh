@@ -133,8 +133,10 @@ k_generate_sweep(const GenArgs a) {
             int cell = p.cell0;
             float off = p.off0;
             const int kb_shift = 1 - p.n_drop;               // kept index of W[0] = cell + kb_shift
+#if DCT_SWEEP_SKIP
             const int first_needed = p.n_drop - 1;           // tap j is kept iff j >= first_needed - cell
             const int last_needed = p.n_drop + B - 1;        //             and j <  last_needed  - cell
+#endif
             // One photo-electron: slide the window to its cell, then add its taps.
             auto add_pe = [&](const u32x4& r, float gap) {
                 int kb = cell + kb_shift;

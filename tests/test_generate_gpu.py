@@ -344,6 +344,62 @@ def test_stats_kernel_matches_numpy():
     assert mean == pytest.approx(x.mean()) and std == pytest.approx(x.std())
 
 
+def _check_stats_against_numpy(g, out, charge_lo, n_charge_bins, pieces=(None,)):
+    from digicamtoy_b200.stats import CubeStats
+    st = CubeStats(g, charge_lo=charge_lo, n_charge_bins=n_charge_bins)
+    edges = [0] + [p for p in pieces if p] + [out.shape[0]]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        st.accumulate(out[lo:hi])
+    r = st.result()
+    c = out.cpu().numpy().astype(np.int64)
+    P, B = c.shape[1], c.shape[2]
+    assert np.array_equal(r['adc_hist'], np.bincount(c.ravel(), minlength=4096))
+    assert np.allclose(r['bin_sum'], c.sum(axis=(0, 1)), rtol=1e-13)
+    assert np.allclose(r['bin_sumsq'], (c ** 2).sum(axis=(0, 1)), rtol=1e-13)
+    assert np.allclose(r['pixel_sum'], c.sum(axis=(0, 2)), rtol=1e-13)
+    assert np.allclose(r['pixel_sumsq'], (c ** 2).sum(axis=(0, 2)), rtol=1e-13)
+    base = np.rint(np.broadcast_to(np.asarray(g.baseline, dtype=np.float32), (P,))).astype(np.int64)
+    charge = c.sum(axis=2) - B * base[None, :]
+    want = np.bincount(np.clip(charge.ravel() - charge_lo, 0, n_charge_bins - 1), minlength=n_charge_bins)
+    if B <= 128:
+        assert np.array_equal(r['charge_hist'], want)
+    x = c.ravel().astype(np.float64)
+    assert np.allclose(r['moments'], [x.sum(), (x ** 2).sum(), (x ** 3).sum(), (x ** 4).sum()], rtol=1e-12)
+
+
+@pytest.mark.parametrize('name,kw,n_events', [
+    ('tile-full-range', dict(n_pixels=200, nsb_rate=0.3, n_photon=5., **ACDC), 150),
+    ('tile-compact-dim', dict(n_pixels=130, n_photon=0., **DARK), 200),                          # B = 92
+    ('tile-compact-bright', dict(n_pixels=130, n_photon=[[3000.]] * 65 + [[40.]] * 65,            # saturating half
+                                 **{**DARK, 'time_signal': 100.}), 200),
+    ('tile-compact-128', dict(n_pixels=33, nsb_rate=0.2, n_photon=300., **{**ACDC, 'time_end': 512}), 120),
+    ('generic-long', dict(n_pixels=20, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 800}), 60),
+    ('generic-odd', dict(n_pixels=20, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 204}), 60),
+])
+def test_stats_kernel_every_dispatch_path(name, kw, n_events):
+    """K3 has three kernels (tile: full-range / compact layout, generic); all must equal NumPy,
+    including samples outside the histogram windows, saturated ones and clamped charges."""
+    g = gen(seed=21, **kw)
+    out = g.generate(n_events)
+    _check_stats_against_numpy(g, out, charge_lo=-300, n_charge_bins=2500, pieces=(n_events // 3,))
+
+
+def test_stats_kernel_synthetic_extremes():
+    """Cubes that no generator config produces: every value of the 12-bit range, in long traces
+    (compact layout: most samples lie outside the CTA histogram window)."""
+    import torch
+    g = gen(n_pixels=130, n_photon=0., seed=1, **DARK)
+    B = g.generate(1).shape[2]
+    assert B == 92
+    rs = np.random.RandomState(3)
+    c = rs.randint(0, 4096, size=(64, 130, B)).astype(np.int16)
+    c[5] = 0
+    c[6] = 4095
+    c[7, :, ::2] = 4095
+    out = torch.from_numpy(c).cuda()
+    _check_stats_against_numpy(g, out, charge_lo=-1000, n_charge_bins=5000)
+
+
 def test_write_calibrate_kernel():
     import torch
     from digicamtoy_b200 import native
