@@ -341,7 +341,7 @@ def run_b200_arm(a):
                             l2='each step writes %.2f GB per GPU into a 2-deep ring (>> 126 MB L2); no input re-read' % (algo_bytes / 1e9),
                             sharding='contiguous global-event ranges per rank; one all-reduce of the statistics at the end'),
                 events_per_s=value / (P * B), roofline=roofline, e2e=e2e, gpu_launches=2 * a.steps,
-                gpu_launches_detail='per step: 1 x k_generate_%s + 1 x k_stats' % gen.kernel,
+                gpu_launches_detail='per step: 1 x k_generate_%s + 1 x k_stats_tile' % gen.kernel,
                 clocks=clocks.summary(w0, w1),
                 validation=dict(mean_adc=stats_result['moments'][0] / max(1, stats_result['n_events'] * P * B),
                                 n_events_reduced=stats_result['n_events'],
