@@ -116,11 +116,11 @@ k_stats(const StatsArgs a) {
 // 2-4 samples of a trace per lane.  This version turns the mapping around:
 //   * thread = trace.  A CTA owns a block of 128 consecutive pixels and walks a slice of events;
 //     each event's 128 rows are one contiguous run of the cube, brought into shared memory with
-//     16-byte cp.async (double buffered) and then read row-wise (odd word stride: conflict-free).
+//     16-byte cp.async (one buffer in the compact layout, else two) and then read row-wise.
 //   * per sample: a plain 16-bit read-modify-write of the thread-private histogram column (window of
 //     STATS_WIN values around the pedestal; the rare sample outside goes to the CTA histogram with
 //     an atomic), and integer sums for the per-trace / per-pixel quantities.
-//   * per bin: warp-wide REDUX of the 32 rows, accumulated by lane (word % 32) in 64-bit registers.
+//   * per bin: a second pass over the tile with lane = word column, accumulated in 64-bit registers.
 //   * per-pixel sums live in registers for the whole slice; raw power sums are derived from the
 //     CTA histogram when it is flushed.
 constexpr int STATS_WIN = 64;
