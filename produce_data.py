@@ -101,6 +101,42 @@ class Writer:
         return self.path
 
 
+def produce_level(config, filename, n_events, seed, device, finish=None):
+    """One (nsb, n_photon) level -> one file (reference produce_data.py:95-142).  ``config`` is the
+    option dictionary: every entry goes into the ``config`` group, and it is the generator's keyword
+    set (unknown keys are ignored there, as in the reference).  ``finish`` (optional) takes the
+    zero-argument function that compresses and closes the file, so a caller can run it on another
+    thread while the GPU generates the next level; the default runs it here."""
+    from digicamtoy_b200 import NTraceGenerator
+    log = logging
+    kwargs = dict(config)
+    kwargs.pop('seed', None)
+    generator = NTraceGenerator(seed=seed, device=device, **kwargs)
+    writer = Writer(filename)
+    for key, val in config.items():                                       # config group (:95-100)
+        writer.put('config/' + key, val)
+    writer.put('config/seed', np.uint64(generator.seed))
+    writer.put('data/true_baseline', generator.true_baseline, compress=True)
+    adc_count, cherenkov_time, cherenkov_photon = generator.generate_host(
+        n_events, first_event=0)                                          # replaces the loop :119-126
+    generator.close()                                                     # (the arrays keep their pinned buffers alive)
+
+    def close():
+        log.info('\t\t-|> Saving data to {}'.format(writer.path))
+        writer.put('data/adc_count', adc_count, compress=True, dtype=np.uint16)
+        writer.put('data/time', cherenkov_time.astype(np.float64), compress=True)
+        writer.put('data/charge', cherenkov_photon.astype(np.float64), compress=True)
+        writer.put('config/date', str(datetime.datetime.now()))
+        path = writer.close()
+        log.info('\t\t-|> File saved! Size = {}'.format(natural_size(os.path.getsize(path))))
+        return path
+
+    if finish is not None:
+        finish(close)
+        return writer.path
+    return close()
+
+
 def main(argv=None):
     log = logging
     options, cli = load_options(argv)
@@ -118,7 +154,6 @@ def main(argv=None):
     log.debug(vars(options))
     log.info('\t\t-|> Create the Monte Carlo data set')
 
-    from digicamtoy_b200 import NTraceGenerator
     options_generator = copy.copy(options)
     events_per_level = options_generator.events_per_level
     base_seed = cli['cli_seed']
@@ -131,26 +166,8 @@ def main(argv=None):
             my_turn = (file_number % world) == rank
             filename = os.path.join(options.output_directory, options.file_basename.format(file_number))
             if my_turn:
-                kwargs = dict(vars(options_generator))
-                kwargs.pop('seed', None)
-                seed = None if base_seed is None else base_seed + file_number
-                generator = NTraceGenerator(seed=seed, device=device, **kwargs)
-                writer = Writer(filename)
-                for key, val in vars(options_generator).items():          # config group (:95-100)
-                    writer.put('config/' + key, val)
-                writer.put('config/seed', np.uint64(generator.seed))
-                writer.put('data/true_baseline', generator.true_baseline, compress=True)
-                adc_count, cherenkov_time, cherenkov_photon = generator.generate_host(
-                    events_per_level, first_event=0)                      # replaces the loop :119-126
-                log.info('\t\t-|> Saving data to {}'.format(writer.path))
-                writer.put('data/adc_count', adc_count, compress=True, dtype=np.uint16)
-                writer.put('data/time', cherenkov_time.astype(np.float64), compress=True)
-                writer.put('data/charge', cherenkov_photon.astype(np.float64), compress=True)
-                writer.put('config/date', str(datetime.datetime.now()))
-                path = writer.close()
-                generator.close()
-                log.info('\t\t-|> File saved! Size = {}'.format(natural_size(os.path.getsize(path))))
-                written.append(path)
+                written.append(produce_level(vars(options_generator), filename, events_per_level,
+                                             None if base_seed is None else base_seed + file_number, device))
             file_number += 1
     return written
 

@@ -77,3 +77,49 @@ def test_sharded_run_equals_single_run():
     assert np.array_equal(acc_i.cpu().numpy(), st_whole._i.cpu().numpy())
     assert np.allclose(acc_f.cpu().numpy(), st_whole._f.cpu().numpy(), rtol=1e-12)
     assert want['n_events'] == n_events
+
+
+def test_batch_launcher_writes_the_commissioning_grid(tmp_path, monkeypatch):
+    """f-4: (n_photon level, NSB level, file id) grid in one process; a file equals what
+    produce_data writes from the YAML that generate.py would have dumped for that job."""
+    import batch_produce as bp
+    import produce_data
+    out = tmp_path / 'mc'
+    common = ['--n_pixels', '48', '--events_per_level', '9', '--ac', '2:3', '--dc', '0:1', '--file_id', '0:1']
+    written = bp.main(common + ['--output_directory', str(out), '--seed', '1000', '--writers', '2',
+                                '--max_in_flight', '2'])
+    assert len(written) == 8
+    names = [os.path.basename(p).replace('.npz', '') for p in written]
+    assert names[:3] == ['ac_2_dc_0_id_0.hdf5', 'ac_2_dc_0_id_1.hdf5', 'ac_2_dc_1_id_0.hdf5']
+    cubes = {}
+    for p, n in zip(written, names):
+        d = _load(p)
+        assert d['data/adc_count'].shape == (9, 48, 92) and d['data/adc_count'].dtype == np.uint16
+        assert d['data/time'].shape == (9, 48, 1)
+        i, j = int(n.split('_')[1]), int(n.split('_')[3])
+        assert float(d['config/n_photon']) == float(i)
+        assert float(d['config/nsb_rate']) == pytest.approx(np.linspace(0.003, 2, 30)[j])
+        assert float(np.ravel(d['config/jitter'])[0]) == 1.155 and int(d['config/time_end']) == 368
+        cubes[n] = d
+    # different files of one level are independent samples; seeds follow (i, j, k)
+    assert not np.array_equal(cubes['ac_2_dc_0_id_0.hdf5']['data/adc_count'],
+                              cubes['ac_2_dc_0_id_1.hdf5']['data/adc_count'])
+    n_dc, n_ids = 30, 2
+    assert int(cubes['ac_3_dc_1_id_1.hdf5']['config/seed']) == 1000 + (3 * n_dc + 1) * n_ids + 1
+    # the NSB level shows: dc_1 (72 MHz) sits above dc_0 (3 MHz)
+    assert cubes['ac_2_dc_1_id_0.hdf5']['data/adc_count'].mean() > cubes['ac_2_dc_0_id_0.hdf5']['data/adc_count'].mean() + 3
+    # the YAML route (generate.py step + produce_data.py -y) gives the same file content
+    cfg_dir = tmp_path / 'commissioning'
+    bp.main(common + ['--write_configs', str(cfg_dir), '--output_directory', str(tmp_path / 'mc2')])
+    seed = 1000 + (3 * n_dc + 1) * n_ids + 1
+    os.makedirs(str(tmp_path / 'mc2'))
+    (path,) = produce_data.main(['-y', str(cfg_dir / 'ac_3_dc_1_id_1.yml'), '--seed', str(seed)])
+    d2 = _load(path)
+    assert np.array_equal(d2['data/adc_count'], cubes['ac_3_dc_1_id_1.hdf5']['data/adc_count'])
+    assert np.array_equal(d2['data/charge'], cubes['ac_3_dc_1_id_1.hdf5']['data/charge'])
+    # a rank of a 4-process launch only takes its share, and nothing is overwritten
+    monkeypatch.setenv('RANK', '1')
+    monkeypatch.setenv('WORLD_SIZE', '4')
+    share = bp.main(common + ['--dry_run', '--output_directory', str(out)])
+    assert [os.path.basename(s) for s in share] == ['ac_2_dc_0_id_1.hdf5', 'ac_3_dc_0_id_1.hdf5']
+    assert bp.main(common + ['--output_directory', str(out)]) == 1

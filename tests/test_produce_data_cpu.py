@@ -78,3 +78,46 @@ def test_named_workloads():
     assert d['time_end'] == 368 and d['nsb_rate'] == 0.003 and d['n_photon'] == 2
     a = workloads.c2_ac_dc(0.66, 100)
     assert a['nsb_rate'] == 0.66 and a['n_photon'] == 100 and a['sigma_e'] == 1.25
+
+
+# ------------------------------------------------------------------ f-4: the commissioning grid launcher
+def test_batch_grid_follows_the_reference_job_array():
+    import batch_produce as bp
+    jobs = bp.job_grid((0, 499), (0, 0), (0, 9))                 # jobs.sh:3-16
+    assert len(jobs) == 5000 and jobs[0] == (0, 0, 0) and jobs[1] == (0, 0, 1) and jobs[10] == (1, 0, 0)
+    assert jobs[-1] == (499, 0, 9)
+    parts = [bp.deal(jobs, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == sorted(jobs) and {len(p) for p in parts} == {625}
+    seeds = {bp.job_seed(100, 30, 10, *j) for j in jobs}
+    assert len(seeds) == len(jobs) and bp.job_seed(None, 30, 10, 1, 2, 3) is None
+
+
+def test_batch_configs_equal_what_generate_py_dumps(tmp_path):
+    """Same keys and values as reference config_files/generate.py:8-71 (restated here)."""
+    import yaml
+    import batch_produce as bp
+    paths = bp.main(['--write_configs', str(tmp_path), '--ac', '3:4', '--file_id', '0:1'])
+    assert [os.path.basename(p) for p in paths] == ['ac_3_dc_0_id_0.yml', 'ac_3_dc_0_id_1.yml',
+                                                    'ac_4_dc_0_id_0.yml', 'ac_4_dc_0_id_1.yml']
+    with open(paths[2]) as f:
+        got = yaml.safe_load(f)
+    P = 1296
+    want = dict(output_directory='/sst1m/MC/digicamtoy/', events_per_level=1000, time_start=0, time_end=368,
+                time_sampling=4, n_pixels=P, gain_nsb=True, poisson=True,
+                pulse_shape_file='utils/pulse_SST-1M_pixel_0.dat', sigma_e=[0.8] * P, sigma_1=[0.8] * P,
+                gain=[5.8] * P, baseline=[200] * P, time_signal=[20] * P, jitter=[1.155] * P,
+                crosstalk=[0.08] * P, nsb_rate=[0.003], n_photon=[4.0], file_basename='ac_4_dc_0_id_0.hdf5')
+    assert got == want
+    n_photons, nsb_rates = bp.light_levels()
+    assert len(n_photons) == 500 and len(nsb_rates) == 30 and nsb_rates[-1] == 2.0 and n_photons[-1] == 499
+
+
+def test_batch_dry_run_and_overwrite_refusal(tmp_path, capsys):
+    import batch_produce as bp
+    files = bp.main(['--dry_run', '--ac', '0:1', '--file_id', '0:2', '--output_directory', str(tmp_path)])
+    assert len(files) == 6 and files[0].endswith('ac_0_dc_0_id_0.hdf5')
+    assert len(capsys.readouterr().out.strip().splitlines()) == 6
+    (tmp_path / 'ac_1_dc_0_id_2.hdf5.npz').write_bytes(b'')
+    assert bp.main(['--ac', '0:1', '--file_id', '0:2', '--output_directory', str(tmp_path)]) == 1
+    with pytest.raises(ValueError):
+        bp.main(['--dry_run', '--ac', '0:500'])
