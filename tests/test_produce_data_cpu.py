@@ -121,3 +121,44 @@ def test_batch_dry_run_and_overwrite_refusal(tmp_path, capsys):
     assert bp.main(['--ac', '0:1', '--file_id', '0:2', '--output_directory', str(tmp_path)]) == 1
     with pytest.raises(ValueError):
         bp.main(['--dry_run', '--ac', '0:500'])
+
+
+def test_hdf5_branch_of_the_writer_with_a_stub_h5py(tmp_path, monkeypatch):
+    """h5py is not in this image; a recording stub checks the calls of the HDF5 branch
+    (groups, gzip-chunked datasets, dtype) -- reference produce_data.py:95-142."""
+    import sys
+    import types
+    calls = []
+
+    class Group:
+        def __init__(self, name):
+            self.name = name
+
+        def create_dataset(self, name, data=None, **kw):
+            calls.append((self.name, name, np.asarray(data).shape if not isinstance(data, str) else 'str', kw))
+
+    class File:
+        def __init__(self, filename, mode):
+            assert mode == 'w'
+            self.filename, self.groups, self.closed = filename, {}, False
+
+        def require_group(self, name):
+            return self.groups.setdefault(name, Group(name))
+
+        def close(self):
+            self.closed = True
+
+    stub = types.ModuleType('h5py')
+    stub.File = File
+    monkeypatch.setitem(sys.modules, 'h5py', stub)
+    w = produce_data.Writer(str(tmp_path / 'f.hdf5'))
+    assert w.h5 is not None and w.path.endswith('f.hdf5')
+    w.put('config/n_pixels', 1296)
+    w.put('config/pulse_shape_file', 'utils/x.dat')
+    w.put('data/adc_count', np.zeros((2, 3, 4), dtype=np.int16), compress=True, dtype=np.uint16)
+    w.put('data/true_baseline', np.zeros(3), compress=True)
+    assert w.close().endswith('f.hdf5') and w.h5.closed
+    assert calls[0] == ('config', 'n_pixels', (), {})
+    assert calls[1] == ('config', 'pulse_shape_file', 'str', {})
+    assert calls[2] == ('data', 'adc_count', (2, 3, 4), dict(chunks=True, compression='gzip', dtype=np.uint16))
+    assert calls[3] == ('data', 'true_baseline', (3,), dict(chunks=True, compression='gzip'))
