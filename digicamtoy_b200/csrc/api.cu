@@ -15,6 +15,7 @@
 #include "device_params.cuh"
 #include "generate.cuh"
 #include "sweep.cuh"
+#include "grid.cuh"
 #include "replay.cuh"
 #include "stats.cuh"
 #include "selftest.cuh"
@@ -66,6 +67,7 @@ struct dct_handle {
     dct::DevParams p{};
     DeviceArena arena;
     int kernel = DCT_KERNEL_SCATTER;
+    float grid_tap[dct::GRID_TAPS] = {0};   // on-grid taps as kernel parameters (K1c)
     int gen_threads = dct::GEN_THREADS;
     bool poly = false;
     bool table_in_smem = false;
@@ -283,6 +285,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         }
     std::vector<float> f_grid((size_t)std::max(1, p.grid_n));
     for (int m = 0; m < p.grid_n; ++m) f_grid[m] = (float)spline_at(c, (m_lo + m) * c->dt);
+    float grid_tap_host[dct::GRID_TAPS] = {0};
+    for (int m = 0; m < p.grid_n && m < dct::GRID_TAPS; ++m) grid_tap_host[m] = f_grid[m];
 
     // ---- one arena
     size_t cur = 0;
@@ -351,7 +355,15 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         return fail(DCT_E_UNSUPPORTED, "trace of %d bins does not fit shared memory", p.B);
     }
     const bool sweep_ok = dct::sweep_supported(p);
+    const bool grid_ok = dct::grid_supported(p);
+    for (int m = 0; m < dct::GRID_TAPS; ++m) h->grid_tap[m] = grid_tap_host[m];
     int want = (int)c->kernel;
+    if (want == DCT_KERNEL_GRID && !grid_ok) {
+        cudaFree(h->arena.base);
+        delete h;
+        return fail(DCT_E_UNSUPPORTED, "grid kernel needs sub_binning > 0 and at most %d on-grid template taps",
+                    dct::GRID_TAPS);
+    }
     if (want == DCT_KERNEL_SWEEP && !sweep_ok) {
         cudaFree(h->arena.base);
         delete h;
@@ -360,7 +372,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                     dct::SWEEP_TAPS, dct::SWEEP_MAX_BINS);
     }
     if (want == DCT_KERNEL_AUTO)
-        want = (sweep_ok && h->mean_pe_per_trace >= dct::SWEEP_MIN_MEAN_PE) ? DCT_KERNEL_SWEEP
+        want = grid_ok ? DCT_KERNEL_GRID
+             : (sweep_ok && h->mean_pe_per_trace >= dct::SWEEP_MIN_MEAN_PE) ? DCT_KERNEL_SWEEP
                                                                             : DCT_KERNEL_SCATTER;
     h->kernel = want;
     g_err[0] = 0;
@@ -392,6 +405,7 @@ int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     a.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
     a.adc = adc; a.sig_time = sig_time; a.sig_charge = sig_charge;
     a.table_in_smem = h->table_in_smem ? 1 : 0;
+    if (h->kernel == DCT_KERNEL_GRID) return dct::launch_grid(h->device, a, h->grid_tap, st, g_err, sizeof(g_err));
     if (h->kernel == DCT_KERNEL_SWEEP) return dct::launch_sweep(h->device, h->sm_count, a, st, g_err, sizeof(g_err));
     if (h->gen_threads == 32)
         return h->poly ? launch_scatter<true, 32>(h, a, st) : launch_scatter<false, 32>(h, a, st);

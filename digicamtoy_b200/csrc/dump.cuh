@@ -50,18 +50,11 @@ __global__ void k_dump_pe(const DumpArgs d) {
                 emit((double)cell * p.dt_d + (double)off + p.t0_d - p.x_lo_d, A);
             }
         } else {
-            BlockReader rd(t.key, STREAM_SUBBIN, 0);
-            const float lam = rate * p.dt;
+            const float lam = rate * p.dt, p0 = __expf(-lam);
             const int n_sim = p.n_drop + p.B;
             for (int bs = 0; bs < n_sim; ++bs) {
-                const int n = poisson(rd, lam);
-                if (n <= 0) continue;
-                const int total = branching_total(rd, n, q.xt);
-                float A = (float)total;
-                if (q.sigma1 > 0.0f) {
-                    const uint32_t r0 = rd.next(), r1 = rd.next();
-                    A = smeared_amplitude(total, normal_one(r0, r1), q.sigma1);
-                }
+                float A;
+                if (!subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) continue;
                 emit(p.t0_d + (double)bs * p.dt_d, A);
             }
         }

@@ -126,4 +126,37 @@ __device__ __noinline__ int branching_total(BlockReader& rd, int n_primary, floa
     return total;
 }
 
+// Poisson(lambda) by sequential inversion of one given uniform; p0 = exp(-lambda) (callers that
+// draw many counts at one mean keep it in a register).  lambda < 12.
+__device__ __forceinline__ int poisson_inv(float u, float lambda, float p0) {
+    float p = p0, cdf = p0;
+    int k = 0;
+    while (u >= cdf && k < 200) {
+        ++k;
+        p *= lambda * __frcp_rn((float)k);
+        cdf += p;
+    }
+    return k;
+}
+
+// On-grid NSB mode, one simulated bin: the part of the count that the bin's own Philox block could
+// not provide (see subbin_cluster in generate.cuh) -- a Poisson mean >= 12 (PTRS needs a variable
+// number of uniforms) or a crosstalk chain that outlived the draws set aside for it.  Reads from
+// `first_block` of STREAM_SUBBIN on: blocks (bs + 1) << 16 ..., which no bin uses as its own block
+// (bins < 65536).  gen < 0: the primaries are still to be drawn; else `gen` pe of the last
+// generation still need their offspring.
+__device__ __noinline__ int subbin_overflow(uint32_t k0, uint32_t k1, uint32_t ev_lo, uint32_t ev_hi, uint32_t pixel,
+                                            uint32_t first_block, float lambda, float mu, int total, int gen) {
+    StreamKey key;
+    key.k0 = k0; key.k1 = k1; key.ev_lo = ev_lo; key.ev_hi = ev_hi; key.pixel = pixel;
+    BlockReader rd(key, STREAM_SUBBIN, first_block);
+    if (gen < 0) total = gen = poisson(rd, lambda);
+    if (mu > 0.0f)
+        for (int g = 0; g < 4096 && gen > 0; ++g) {
+            gen = poisson(rd, mu * (float)gen);
+            total += gen;
+        }
+    return total;
+}
+
 }  // namespace dct

@@ -18,8 +18,8 @@ LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
 CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
 
 DCT_ABI_VERSION = 1
-KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP = 0, 1, 2
-KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep'}
+KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP, KERNEL_GRID = 0, 1, 2, 3
+KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep', KERNEL_GRID: 'grid'}
 
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',

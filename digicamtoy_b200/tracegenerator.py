@@ -24,7 +24,8 @@ import numpy as np
 from . import native
 from .params import ARTIFICIAL_BACKWARD_TIME, build_params, evaluate_template, resolve_pulse_shape_file
 
-_KERNELS = {'auto': native.KERNEL_AUTO, 'scatter': native.KERNEL_SCATTER, 'sweep': native.KERNEL_SWEEP}
+_KERNELS = {'auto': native.KERNEL_AUTO, 'scatter': native.KERNEL_SCATTER, 'sweep': native.KERNEL_SWEEP,
+            'grid': native.KERNEL_GRID}
 
 
 def _torch():

@@ -44,11 +44,13 @@ enum {
 };
 
 /* Kernel selection for dct_generate.  DCT_KERNEL_AUTO: the sweep kernel whenever the configuration
- * supports it (22-tap / 8-phase polyphase table, continuous NSB), else the scatter kernel. */
+ * supports it (22-tap / 8-phase polyphase table, continuous NSB), the grid kernel for sub_binning > 0
+ * (at most 24 on-grid template taps), else the scatter kernel. */
 enum {
     DCT_KERNEL_AUTO = 0,
     DCT_KERNEL_SCATTER = 1,  /* shared-memory accumulators, any template / sampling           */
-    DCT_KERNEL_SWEEP = 2     /* time-ordered register window (default template at 4 ns sampling) */
+    DCT_KERNEL_SWEEP = 2,    /* time-ordered register window (default template at 4 ns sampling) */
+    DCT_KERNEL_GRID = 3      /* sub_binning > 0 only: fixed on-grid taps, register window          */
 };
 
 /* Everything NTraceGenerator.__init__ derives (reference :52-157), already transformed on the
@@ -95,7 +97,7 @@ DCT_API const char* dct_last_error(void);
 DCT_API int  dct_create(const dct_config* cfg, int device, dct_handle** out);
 DCT_API void dct_destroy(dct_handle* h);
 
-/* Which kernel dct_generate will use for this config (DCT_KERNEL_SCATTER / _SWEEP). */
+/* Which kernel dct_generate will use for this config (DCT_KERNEL_SCATTER / _SWEEP / _GRID). */
 DCT_API int dct_selected_kernel(const dct_handle* h);
 
 /* replaces n_events calls of NTraceGenerator.next() (:201-226 -> stages :228-381) for global

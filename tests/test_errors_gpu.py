@@ -41,6 +41,8 @@ def test_python_surface_raises_value_errors():
         NTraceGenerator(n_pixels=4, kernel='nope')
     with pytest.raises(ValueError):                           # sweep kernel only exists for the 22-tap / 8-phase table
         NTraceGenerator(n_pixels=4, kernel='sweep', pulse_shape_file='utils/pulse_SST-1M_AfterPreampLowGain.dat')
+    with pytest.raises(ValueError):                           # grid kernel only exists for sub_binning > 0
+        NTraceGenerator(n_pixels=4, kernel='grid')
     with pytest.raises(ValueError):
         NTraceGenerator(n_pixels=4, device='cpu')
     with pytest.raises(FileNotFoundError):

@@ -63,6 +63,35 @@ def test_sweep_scatter_identical_with_per_pixel_rates_and_dark_window():
     assert np.array_equal(cube(a, 30), cube(b, 30))
 
 
+@pytest.mark.parametrize('kw', [
+    dict(nsb_rate=1.0, n_photon=100., **ACDC),
+    dict(nsb_rate=0.125, n_photon=0., **ACDC),
+    dict(nsb_rate=3.5, n_photon=2., **ACDC),                               # Poisson mean 14 per bin: PTRS branch
+    dict(n_photon=2, **{**DARK, 'sigma_1': 0., 'nsb_rate': np.concatenate([np.zeros(3), np.logspace(-3, 0.6, 61)])}),
+    dict(nsb_rate=0.5, n_photon=5., **{**ACDC, 'crosstalk': 0.5}),           # long crosstalk chains: overflow blocks
+])
+def test_grid_and_scatter_kernels_are_bit_identical_for_on_grid_nsb(kw):
+    """sub_binning > 0: the register-window kernel (default) against the generic one."""
+    P = 64 if np.ndim(kw['nsb_rate']) else 200
+    a = gen(n_pixels=P, sub_binning=1, seed=5, kernel='scatter', **kw)
+    b = gen(n_pixels=P, sub_binning=1, seed=5, **kw)
+    assert a.kernel == 'scatter' and b.kernel == 'grid'
+    ca, ta, qa = cube(a, 24, truth=True)
+    cb, tb, qb = cube(b, 24, truth=True)
+    assert np.array_equal(ca, cb)
+    assert np.array_equal(ta, tb) and np.array_equal(qa, qb)
+    assert ca.std() > 0
+
+
+def test_grid_kernel_falls_back_when_the_template_has_too_many_on_grid_taps():
+    g = gen(n_pixels=8, sub_binning=1, nsb_rate=0.3, seed=1, time_start=0, time_end=100, time_sampling=2)
+    assert g.kernel == 'scatter'                                           # 88 ns / 2 ns = 45 taps > 24
+    assert cube(g, 4).shape == (4, 8, 50)
+    g = gen(n_pixels=8, sub_binning=1, nsb_rate=0.3, seed=1,               # template starts at -8 ns
+            pulse_shape_file='utils/pulse_SST-1M_AfterPreampLowGain.dat', **ACDC)
+    assert g.kernel == 'scatter' and cube(g, 4).std() > 0
+
+
 def test_host_path_equals_device_path():
     g = gen(n_pixels=1296, nsb_rate=0.125, n_photon=10., seed=3, **ACDC)
     dev, t, q = cube(g, 700, truth=True)           # > one 64 MiB chunk of the host pipeline
@@ -435,6 +464,76 @@ def test_reference_arithmetic_on_gpu_drawn_photoelectrons_reproduces_gpu_adc(ker
         assert d.max() <= 1, d.max()
         n_diff += int((d != 0).sum())
     assert n_diff <= 2e-3 * adc.size, n_diff
+
+
+@pytest.mark.parametrize('kernel', ['scatter', 'grid'])
+@pytest.mark.parametrize('rate,xt', [(1.0, 0.08), (0.125, 0.08), (0.4, 0.5), (3.5, 0.08)])
+def test_reference_arithmetic_reproduces_gpu_adc_in_on_grid_mode(kernel, rate, xt):
+    """Same closed loop for sub_binning > 0 (reference :259-267): the pe sit on the simulated samples,
+    dt apart from time_start - 40 ns on; counts per bin are Poisson(rate dt), clusters carry their
+    crosstalk progeny (long chains and Poisson means >= 12 take the overflow draws)."""
+    P = 96
+    kw = dict(n_pixels=P, nsb_rate=rate, n_photon=5., sub_binning=1, **{**ACDC, 'crosstalk': xt})
+    g = gen(seed=77, kernel=kernel, saturate=None, **kw)
+    assert g.kernel == kernel
+    n_ev = 6
+    adc, t, q = cube(g, n_ev, truth=True)
+    pe = g.trace_pe(n_ev, first_event=0)
+    cfg = orc.make_config(**kw)
+    # occupied bins: P(n > 0) = 1 - exp(-rate dt); every pe time is on the grid
+    occupied = pe['count'].mean() / 60.0
+    assert occupied == pytest.approx(1 - np.exp(-rate * 4), abs=0.02)
+    n_diff = 0
+    amp_sum = 0.0
+    for e in range(n_ev):
+        tt = pe['time'][e]
+        for pix in range(P):
+            k = pe['count'][e, pix]
+            on_grid = (tt[pix, :k] + 40.0) / 4.0
+            assert np.array_equal(on_grid, np.round(on_grid))
+            amp_sum += pe['amplitude'][e, pix, :k].sum()
+        want = orc.shape_and_digitise(cfg, tt, pe['amplitude'][e].astype(np.float64),
+                                      t[e].astype(np.float64), q[e].astype(np.float64),
+                                      pe['noise'][e].astype(np.float64))
+        d = np.abs(adc[e].astype(np.int64) - want.astype(np.int64))
+        assert d.max() <= 1, d.max()
+        n_diff += int((d != 0).sum())
+    assert n_diff <= 2e-3 * adc.size, n_diff
+    # total charge per trace: rate dt pe per bin, each 1 / (1 - xt) after crosstalk
+    want_sum = n_ev * P * 60 * rate * 4 / (1 - xt)
+    assert amp_sum == pytest.approx(want_sum, rel=0.04 if xt < 0.3 else 0.08)
+
+
+@pytest.mark.parametrize('rate,xt', [(1.0, 0.08), (0.125, 0.08), (0.5, 0.4)])
+def test_on_grid_mode_high_statistics_against_closed_form(rate, xt):
+    """sub_binning > 0 at 1.3e7 traces: per-bin mean and variance of the compound Poisson sum
+    V_b = g sum_m h(m dt) S_(b-m), S = clusters of Poisson(rate dt) primaries (:259-267, :306-312)."""
+    from digicamtoy_b200.stats import CubeStats
+    P, E, chunk = 64, 200_000, 20_000
+    kw = dict(n_pixels=P, nsb_rate=rate, n_photon=0., sub_binning=1, **{**ACDC, 'crosstalk': xt})
+    g = gen(seed=2024, **kw)                                   # (no sample comes near 0 or 4095 here)
+    assert g.kernel == 'grid'
+    st = CubeStats(g)
+    for i in range(E // chunk):
+        st.accumulate(g.generate(chunk, first_event=i * chunk))
+    r = st.result()
+    n = E * P
+    mean = r['bin_sum'] / n
+    var = r['bin_sumsq'] / n - mean ** 2
+    cfg = orc.make_config(**kw)
+    B, n_drop, dt = 50, 10, 4.0
+    h = np.asarray(cfg.pulse_template(np.arange(23) * dt), dtype=np.float64)
+    lam = cfg.nsb_rate[0] * dt
+    m1 = 1 / (1 - xt)
+    m2 = xt / (1 - xt) ** 3 + m1 ** 2 + cfg.sigma_1[0] ** 2 * m1
+    want_mean, want_var = np.zeros(B), np.zeros(B)
+    for b in range(B):
+        taps = h[:min(23, b + n_drop + 1)]                     # pe only exist from simulated bin 0 on
+        want_mean[b] = cfg.baseline[0] + cfg.gain[0] * lam * m1 * taps.sum()
+        want_var[b] = cfg.gain[0] ** 2 * lam * m2 * (taps ** 2).sum() + cfg.sigma_e[0] ** 2 + 1 / 12
+    z = (mean - want_mean) / np.sqrt(want_var / n)
+    assert np.abs(z).max() < 5, z
+    assert np.abs(var / want_var - 1).max() < 0.01, (var / want_var)
 
 
 def test_pe_list_attributes_of_the_iterator():
