@@ -144,13 +144,16 @@ __device__ __forceinline__ float smeared_amplitude(int n, float z, float sigma1)
 // and the 27 bits the uniforms do not use (low 9 of .x, .z, .w) -> second generation.  A cluster
 // that is still alive then (2 % of the non-empty bins at 1 GHz, xt = 0.08) takes generations 3-6
 // from block (bs + 1) << 16, and whatever is left goes to subbin_overflow.   p0 = exp(-lam).
+// cdf (optional): this trace's poisson_table_fill(lam) with stride cdf_stride -- same counts, no loop.
 __device__ __forceinline__ bool subbin_cluster(const StreamKey& key, uint32_t bs, float lam, float p0,
-                                               const PixelNsb& q, float& A) {
+                                               const PixelNsb& q, float& A,
+                                               const float* cdf = nullptr, int cdf_stride = 1) {
     const u32x4 r = draw_block(key, STREAM_SUBBIN, bs);
     int total = 0, gen = -1;
     uint32_t overflow_block = (bs + 1u) << 16;
     if (lam < 12.0f) {
-        total = gen = poisson_inv(u01_open1(r.x), lam, p0);
+        total = gen = cdf ? poisson_table_draw(u01_open1(r.x), cdf, cdf_stride, lam, p0)
+                          : poisson_inv(u01_open1(r.x), lam, p0);
         if (total == 0) return false;
         if (q.xt > 0.0f) {
             auto next_generation = [&](uint32_t bits) {          // no-op once the cluster has died out

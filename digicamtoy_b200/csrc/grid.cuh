@@ -23,9 +23,13 @@ struct GridArgs {
     float tap[GRID_TAPS];                    // h((grid_m_lo + j) * dt), zero beyond grid_n
 };
 
+__host__ __device__ inline size_t grid_smem_bytes(int B) {    // rows + one Poisson table per trace
+    return gen_smem_bytes(B, 0, GRID_THREADS) + (size_t)GRID_THREADS * POISSON_TABLE * sizeof(float);
+}
+
 __host__ __device__ inline bool grid_supported(const DevParams& p) {
     return p.sub_binning > 0 && p.grid_n >= 1 && p.grid_n <= GRID_TAPS && p.grid_m_lo >= 0 &&
-           gen_smem_bytes(p.B, 0, GRID_THREADS) <= 227 * 1024;
+           grid_smem_bytes(p.B) <= 227 * 1024;
 }
 
 #ifndef DCT_GRID_MIN_BLOCKS
@@ -42,6 +46,7 @@ k_generate_grid(const GridArgs ga) {
     const int B = p.B;
     float* rows = reinterpret_cast<float*>(smem_raw);
     float* row = rows + tid * row_stride(B);
+    float* cdf = rows + NT * row_stride(B) + tid;            // this trace's Poisson table, stride NT
     for (int b = 0; b < B; ++b) row[b] = 0.0f;
     __syncthreads();
 
@@ -55,11 +60,12 @@ k_generate_grid(const GridArgs ga) {
 #pragma unroll
             for (int j = 0; j < GRID_TAPS; ++j) W[j] = 0.0f;
             const float lam = rate * p.dt, p0 = __expf(-lam);
+            if (lam < 12.0f) poisson_table_fill(cdf, NT, lam, p0);   // (only this thread reads it)
             const int n_sim = p.n_drop + B;
             int kb = p.grid_m_lo - p.n_drop;                 // kept index of W[0]
             for (int bs = 0; bs < n_sim; ++bs, ++kb) {
                 float A;
-                if (subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) {
+                if (subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A, cdf, NT)) {
 #pragma unroll
                     for (int j = 0; j < GRID_TAPS; ++j) W[j] = __fmaf_rn(A, ga.tap[j], W[j]);
                 }
@@ -79,7 +85,7 @@ k_generate_grid(const GridArgs ga) {
 
 inline int launch_grid(int device, const GenArgs& a, const float* taps, cudaStream_t st, char* err, size_t err_len) {
     auto kern = k_generate_grid<GRID_THREADS>;
-    const size_t smem = gen_smem_bytes(a.p.B, 0, GRID_THREADS);
+    const size_t smem = grid_smem_bytes(a.p.B);
     static thread_local size_t configured[16] = {0};
     if (smem > 48 * 1024 && configured[device & 15] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -139,6 +139,42 @@ __device__ __forceinline__ int poisson_inv(float u, float lambda, float p0) {
     return k;
 }
 
+// The same inversion when many counts are drawn at one mean: the first POISSON_TABLE cumulative
+// probabilities are tabulated once (same float recurrence, so the result is the one poisson_inv
+// gives) and searched without a data-dependent loop.  cdf[i] = P(k <= i); stride in floats.
+constexpr int POISSON_TABLE = 16;
+
+__device__ __forceinline__ void poisson_table_fill(float* cdf, int stride, float lambda, float p0) {
+    float p = p0, c = p0;
+    cdf[0] = c;
+    for (int k = 1; k < POISSON_TABLE; ++k) {
+        p *= lambda * __frcp_rn((float)k);
+        c += p;
+        cdf[k * stride] = c;
+    }
+}
+
+__device__ __forceinline__ int poisson_table_draw(float u, const float* cdf, int stride, float lambda, float p0) {
+    // number of entries among cdf[0..14] that are <= u (the table is non-decreasing)
+    int k = (u >= cdf[7 * stride]) ? 8 : 0;
+    k += (u >= cdf[(k + 3) * stride]) ? 4 : 0;
+    k += (u >= cdf[(k + 1) * stride]) ? 2 : 0;
+    k += (u >= cdf[k * stride]) ? 1 : 0;
+    if (k == POISSON_TABLE - 1 && u >= cdf[(POISSON_TABLE - 1) * stride]) {
+        // beyond the table: carry the recurrence on from its last entry
+        float p = p0;
+        for (int i = 1; i < POISSON_TABLE; ++i) p *= lambda * __frcp_rn((float)i);
+        float c = cdf[(POISSON_TABLE - 1) * stride];
+        k = POISSON_TABLE - 1;
+        while (u >= c && k < 200) {
+            ++k;
+            p *= lambda * __frcp_rn((float)k);
+            c += p;
+        }
+    }
+    return k;
+}
+
 // On-grid NSB mode, one simulated bin: the part of the count that the bin's own Philox block could
 // not provide (see subbin_cluster in generate.cuh) -- a Poisson mean >= 12 (PTRS needs a variable
 // number of uniforms) or a crosstalk chain that outlived the draws set aside for it.  Reads from
