@@ -162,3 +162,18 @@ def test_hdf5_branch_of_the_writer_with_a_stub_h5py(tmp_path, monkeypatch):
     assert calls[1] == ('config', 'pulse_shape_file', 'str', {})
     assert calls[2] == ('data', 'adc_count', (2, 3, 4), dict(chunks=True, compression='gzip', dtype=np.uint16))
     assert calls[3] == ('data', 'true_baseline', (3,), dict(chunks=True, compression='gzip'))
+
+
+def test_batch_ranks_partition_the_grid(tmp_path, monkeypatch, capsys):
+    """Under torchrun every rank walks its own share: together exactly the grid, no file twice."""
+    import batch_produce as bp
+    seen = []
+    for rank in range(3):
+        monkeypatch.setenv('RANK', str(rank))
+        monkeypatch.setenv('WORLD_SIZE', '3')
+        seen.append(bp.main(['--dry_run', '--ac', '5:8', '--file_id', '0:4', '--output_directory', str(tmp_path)]))
+    capsys.readouterr()
+    flat = [f for part in seen for f in part]
+    assert len(flat) == 20 and len(set(flat)) == 20
+    assert {len(part) for part in seen} == {6, 7}
+    assert os.path.basename(seen[1][0]) == 'ac_5_dc_0_id_1.hdf5'
