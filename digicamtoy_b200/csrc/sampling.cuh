@@ -10,6 +10,14 @@
 #pragma once
 #include "philox.cuh"
 
+// -DDCT_EXP_NO_TAIL_STOP=1 builds the inversion loops without their tail stop (to show what
+// tests/test_generate_gpu.py::test_inversion_samplers_stop_in_the_tail_for_the_largest_uniforms guards).
+#if DCT_EXP_NO_TAIL_STOP
+#define DCT_TAIL_STOP(next, cur)
+#else
+#define DCT_TAIL_STOP(next, cur) if ((next) == (cur)) break;
+#endif
+
 namespace dct {
 
 __device__ __forceinline__ float fast_lg2(float x) {
@@ -61,8 +69,13 @@ __device__ __noinline__ int borel_search(float u, float mu) {
     while (u >= cdf && n < 256) {
         const float fn = (float)n;
         p *= step * __powf(1.0f + 1.0f / fn, fn - 1.0f);
-        cdf += p;
         ++n;
+        // The float sum of the masses can stop a few 1e-8 short of 1: once a term no longer moves
+        // it, the largest uniforms (1 - 2^-23) would otherwise run to the cap -- a 256-pe cluster
+        // once per ~1e7 draws.  The value reached here is where the tail has that probability.
+        const float next = cdf + p;
+        DCT_TAIL_STOP(next, cdf)
+        cdf = next;
     }
     return n;
 }
@@ -108,7 +121,9 @@ __device__ __forceinline__ int poisson(BlockReader& rd, float lambda) {
     while (u >= cdf && k < 200) {
         ++k;
         p *= lambda / (float)k;
-        cdf += p;
+        const float next = cdf + p;
+        DCT_TAIL_STOP(next, cdf)                  // tail below float resolution (see borel_search)
+        cdf = next;
     }
     return k;
 }
@@ -134,7 +149,9 @@ __device__ __forceinline__ int poisson_inv(float u, float lambda, float p0) {
     while (u >= cdf && k < 200) {
         ++k;
         p *= lambda * __frcp_rn((float)k);
-        cdf += p;
+        const float next = cdf + p;
+        DCT_TAIL_STOP(next, cdf)                  // tail below float resolution (see borel_search)
+        cdf = next;
     }
     return k;
 }
@@ -146,11 +163,14 @@ constexpr int POISSON_TABLE = 16;
 
 __device__ __forceinline__ void poisson_table_fill(float* cdf, int stride, float lambda, float p0) {
     float p = p0, c = p0;
+    bool live = true;                        // poisson_inv stops at the first term that no longer moves the sum
     cdf[0] = c;
     for (int k = 1; k < POISSON_TABLE; ++k) {
         p *= lambda * __frcp_rn((float)k);
-        c += p;
-        cdf[k * stride] = c;
+        const float next = c + p;
+        live = live && next != c;
+        c = next;
+        cdf[k * stride] = live ? c : __int_as_float(0x7f800000);   // +inf: no uniform gets past it
     }
 }
 
@@ -169,7 +189,9 @@ __device__ __forceinline__ int poisson_table_draw(float u, const float* cdf, int
         while (u >= c && k < 200) {
             ++k;
             p *= lambda * __frcp_rn((float)k);
-            c += p;
+            const float next = c + p;
+            DCT_TAIL_STOP(next, c)
+            c = next;
         }
     }
     return k;

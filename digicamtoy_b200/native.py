@@ -178,7 +178,8 @@ def write_calibrate(buf_ptr, n, stream=None):
     check(load_library().dct_write_calibrate(buf_ptr, n, stream))
 
 
-SAMPLERS = {'normal': 0, 'exp_gap': 1, 'borel': 2, 'poisson': 3, 'branching': 4, 'uniform': 5}
+SAMPLERS = {'normal': 0, 'exp_gap': 1, 'borel': 2, 'poisson': 3, 'branching': 4, 'uniform': 5,
+            'poisson_top': 6, 'borel_top': 7, 'poisson_inv_top': 8, 'poisson_table_top': 9}
 
 
 def test_sample(kind, a, b, seed, n, out_ptr, stream=None):

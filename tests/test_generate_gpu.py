@@ -165,6 +165,31 @@ def test_poisson_sampler(lam):
     assert sps.chi2.sf(chi2, ok.sum() - 1) > 1e-4, (lam, chi2, ok.sum())
 
 
+def test_inversion_samplers_stop_in_the_tail_for_the_largest_uniforms():
+    """The float sum of a pmf can end a few 1e-8 below 1.  A search that only stops at
+    ``u < cdf`` then runs to its cap for the largest uniforms (1 - 2^-23 ...): a 200-pe count or a
+    256-pe crosstalk cluster once per ~1e7 draws.  Feed the samplers exactly those uniforms."""
+    n = 64
+    for kind in ('poisson_top', 'poisson_inv_top', 'poisson_table_top'):
+        for lam in np.concatenate([np.linspace(0.004, 11.99, 300), [0.08, 0.32, 0.5, 4.0]]):
+            v = _sample(kind, lam, 0, n)
+            top = sps.poisson.isf(1e-10, lam) + 2
+            assert v.max() <= top, (kind, lam, v.max(), top)
+            assert v.min() >= sps.poisson.isf(2.0 ** -23 * n * 4, lam) - 1, (kind, lam, v.min())
+            assert np.all(np.diff(v) <= 0)                         # smaller uniform, smaller count
+    for lam in np.linspace(0.004, 11.99, 300):                     # the three forms agree draw by draw
+        a, b, c = (_sample(k, lam, 0, n) for k in ('poisson_inv_top', 'poisson_table_top', 'poisson_top'))
+        assert np.array_equal(a, b), lam
+        assert np.abs(a - c).max() <= 3, lam                       # poisson() divides, the others multiply by 1/k:
+                                                                   # at 1e-7 from the top the rounding shows
+    for xt in np.concatenate([np.linspace(0.005, 0.5, 100), [0.08]]):
+        v = _sample('borel_top', xt, 0, n)
+        tail = 1 - np.cumsum(orc.borel_pmf(xt, 400))
+        top = np.arange(1, 401)[np.argmax(tail < 1e-11)] + 2
+        assert v.max() <= top, (xt, v.max(), top)
+        assert np.all(np.diff(v) <= 0)
+
+
 @pytest.mark.parametrize('n0,xt', [(1, 0.08), (7, 0.1), (100, 0.08), (3000, 0.3)])
 def test_branching_total_is_generalised_poisson(n0, xt):
     s = _sample('branching', a=xt, b=n0, n=200000)
