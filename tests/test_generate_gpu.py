@@ -44,6 +44,22 @@ def test_chunking_and_offsets_do_not_change_bits(kernel):
     assert not np.array_equal(cube(g3, 40), whole)
 
 
+@pytest.mark.parametrize('kernel', ['scatter', 'sweep'])
+def test_event_index_beyond_32_bits(kernel):
+    """The global event index is 56 bits wide in the Philox counter (low word + 24 high bits):
+    a range that crosses 2^32 is the concatenation of its parts, and event 2^32 is not event 0."""
+    g = gen(n_pixels=40, nsb_rate=0.3, n_photon=3., seed=3, kernel=kernel, **ACDC)
+    edge = 1 << 32
+    whole = cube(g, 6, first_event=edge - 3)
+    assert np.array_equal(whole[:3], cube(g, 3, first_event=edge - 3))
+    assert np.array_equal(whole[3:], cube(g, 3, first_event=edge))
+    assert not np.array_equal(whole[3:], cube(g, 3, first_event=0))
+    far = cube(g, 2, first_event=(1 << 55) + 5)
+    assert far.std() > 0 and not np.array_equal(far, cube(g, 2, first_event=5))
+    with pytest.raises(ValueError):
+        g.generate(2, first_event=(1 << 56) - 1)
+
+
 @pytest.mark.parametrize('rate,npe', [(1.0, 100.), (0.125, 10.), (0.04, 0.), (0.003, 1.)])
 def test_sweep_and_scatter_kernels_are_bit_identical(rate, npe):
     a = gen(n_pixels=200, nsb_rate=rate, n_photon=npe, seed=5, kernel='scatter', **ACDC)
