@@ -94,6 +94,19 @@ __host__ __device__ __forceinline__ u32x4 draw_block(const StreamKey& s, uint32_
 __device__ __forceinline__ float u01_open0(uint32_t r) {
     return __uint_as_float(0x3f800000u | (r >> 9)) - (1.0f - 5.9604645e-08f);   // (0,1]
 }
+// Uniform in (0, 1] on a 2^-32 grid near 0 (the float conversion keeps 24 significant bits, so the
+// resolution is relative).  For Box-Muller radii: the 23-bit form stops at sqrt(-2 ln 2^-24) =
+// 5.77 sigma -- eight samples in 1e9 too few beyond it; this one reaches 6.77 sigma (1.3e-11).
+#ifndef DCT_NORMAL_TAIL32
+#define DCT_NORMAL_TAIL32 1
+#endif
+__device__ __forceinline__ float u01_tail(uint32_t r) {
+#if DCT_NORMAL_TAIL32
+    return fmaf(__uint2float_rn(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r + 0.5) 2^-32
+#else
+    return u01_open0(r);
+#endif
+}
 // Uniform in [0, 1).
 __device__ __forceinline__ float u01_open1(uint32_t r) {
     return __uint_as_float(0x3f800000u | (r >> 9)) - 1.0f;

@@ -41,7 +41,7 @@ constexpr float NEG_LN2 = -0.69314718056f;
 // Box-Muller; both outputs are independent N(0, s2) where the variance scale s2 multiplies -2 ln u
 // under the root (lets callers fold sqrt(n) of the gain smearing into the same MUFU.SQRT).
 __device__ __forceinline__ void normal_pair(uint32_t r0, uint32_t r1, float& z0, float& z1) {
-    const float rad = fast_sqrt(fast_lg2(u01_open0(r0)) * NEG_2LN2);
+    const float rad = fast_sqrt(fast_lg2(u01_tail(r0)) * NEG_2LN2);
     float s, c;
     __sincosf(random_angle(r1), &s, &c);
     z0 = rad * c;
@@ -50,7 +50,7 @@ __device__ __forceinline__ void normal_pair(uint32_t r0, uint32_t r1, float& z0,
 
 // One N(0, var_scale) draw: cos(angle) * sqrt(-2 var_scale ln u).
 __device__ __forceinline__ float normal_scaled(uint32_t r0, uint32_t r1, float var_scale) {
-    return fast_sqrt(fast_lg2(u01_open0(r0)) * (NEG_2LN2 * var_scale)) * __cosf(random_angle(r1));
+    return fast_sqrt(fast_lg2(u01_tail(r0)) * (NEG_2LN2 * var_scale)) * __cosf(random_angle(r1));
 }
 __device__ __forceinline__ float normal_one(uint32_t r0, uint32_t r1) { return normal_scaled(r0, r1, 1.0f); }
 

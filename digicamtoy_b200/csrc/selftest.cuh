@@ -10,7 +10,8 @@ enum : uint32_t { SAMPLE_NORMAL = 0, SAMPLE_EXP_GAP = 1, SAMPLE_BOREL = 2, SAMPL
                   // the inversion samplers fed with the LARGEST uniforms, 1 - (i+1) 2^-23: the float sum
                   // of the masses may end below them and the search must still stop in the tail
                   SAMPLE_POISSON_TOP = 6, SAMPLE_BOREL_TOP = 7, SAMPLE_POISSON_INV_TOP = 8,
-                  SAMPLE_POISSON_TABLE_TOP = 9 };
+                  SAMPLE_POISSON_TABLE_TOP = 9,
+                  SAMPLE_NORMAL_RADIUS_TOP = 10 };   // Box-Muller radius for the SMALLEST uniforms (r0 = i)
 
 __global__ void k_test_sample(uint32_t kind, float a, float b, uint32_t k0, uint32_t k1, uint32_t n,
                               float* out) {
@@ -53,6 +54,7 @@ __global__ void k_test_sample(uint32_t kind, float a, float b, uint32_t k0, uint
             rd.buf.x = 0xFFFFFFFFu - (i << 9); rd.have = 1;
             v = (float)poisson(rd, a);
         } break;
+        case SAMPLE_NORMAL_RADIUS_TOP: { float z0, z1; normal_pair(i, 0x80000000u, z0, z1); v = sqrtf(z0 * z0 + z1 * z1); } break;
         case SAMPLE_POISSON_INV_TOP: v = (float)poisson_inv(u01_open1(0xFFFFFFFFu - (i << 9)), a, __expf(-a)); break;
         case SAMPLE_POISSON_TABLE_TOP: {
             float tab[POISSON_TABLE];

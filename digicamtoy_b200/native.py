@@ -179,7 +179,8 @@ def write_calibrate(buf_ptr, n, stream=None):
 
 
 SAMPLERS = {'normal': 0, 'exp_gap': 1, 'borel': 2, 'poisson': 3, 'branching': 4, 'uniform': 5,
-            'poisson_top': 6, 'borel_top': 7, 'poisson_inv_top': 8, 'poisson_table_top': 9}
+            'poisson_top': 6, 'borel_top': 7, 'poisson_inv_top': 8, 'poisson_table_top': 9,
+            'normal_radius_top': 10}
 
 
 def test_sample(kind, a, b, seed, n, out_ptr, stream=None):

@@ -142,6 +142,31 @@ def test_uniform_and_normal_samplers():
     assert abs(sps.kurtosis(z)) < 0.05
 
 
+def test_normal_sampler_reaches_beyond_six_sigma():
+    """Box-Muller on a 23-bit uniform ends at sqrt(-2 ln 2^-24) = 5.77 sigma.  The radius uniform
+    uses all 32 bits (2^-32 grid near 0): up to 6.77 sigma, and the right number of samples between."""
+    import torch
+    from digicamtoy_b200 import native
+    r = _sample('normal_radius_top', n=1024)
+    want = np.sqrt(-2 * np.log((np.arange(1024) + 0.5) * 2.0 ** -32))                  # 6.76 ... 5.52
+    assert np.abs(r - want).max() < 2e-3 and r[0] > 6.75
+    assert np.all(np.diff(r) <= 1e-6)
+    n, chunks = 1 << 28, 8
+    beyond55, beyond577, biggest = 0, 0, 0.0
+    out = torch.empty(n, dtype=torch.float32, device='cuda')
+    for c in range(chunks):
+        native.test_sample('normal', 0, 0, 1000 + c, n, out.data_ptr())
+        a = out.abs()
+        beyond55 += int((a > 5.5).sum())
+        beyond577 += int((a > 5.768).sum())
+        biggest = max(biggest, float(a.max()))
+    total = n * chunks                                               # 2.1e9 normals
+    want55, want577 = total * 2 * sps.norm.sf(5.5), total * 2 * sps.norm.sf(5.768)     # 82 and 17
+    assert abs(beyond55 - want55) < 5 * np.sqrt(want55), (beyond55, want55)
+    assert abs(beyond577 - want577) < 5 * np.sqrt(want577) and beyond577 > 0, (beyond577, want577)
+    assert 5.768 < biggest < 6.78
+
+
 def test_exponential_gap_sampler():
     x = _sample('exp_gap', a=2.5)
     assert sps.kstest(x, 'expon', args=(0, 2.5)).pvalue > 1e-3
