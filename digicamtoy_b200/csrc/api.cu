@@ -556,7 +556,7 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
     if (fast) {
         // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
         // the charge of a trace that holds nothing but that pedestal shift
-        const int win_lo = (int)std::floor(h->mean_true_baseline) - dct::STATS_WIN / 2 + 4;
+        const int win_lo = (int)std::floor(h->mean_true_baseline) - dct::STATS_WIN / 4;   // pulses only go up
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
         int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
         charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));

@@ -118,12 +118,15 @@ k_stats(const StatsArgs a) {
 //     each event's 128 rows are one contiguous run of the cube, brought into shared memory with
 //     16-byte cp.async (one buffer in the compact layout, else two) and then read row-wise.
 //   * per sample: a plain 16-bit read-modify-write of the thread-private histogram column (window of
-//     STATS_WIN values around the pedestal; the rare sample outside goes to the CTA histogram with
+//     STATS_WIN (16) values around the pedestal; the rare sample outside goes to the CTA histogram with
 //     an atomic), and integer sums for the per-trace / per-pixel quantities.
 //   * per bin: a second pass over the tile with lane = word column, accumulated in 64-bit registers.
 //   * per-pixel sums live in registers for the whole slice; raw power sums are derived from the
 //     CTA histogram when it is flushed.
-constexpr int STATS_WIN = 64;
+#ifndef DCT_STATS_WIN
+#define DCT_STATS_WIN 16      // measured (profiles/r01/k3_compact_variants.txt): 64 -> 16 values frees 12 KB per CTA;
+#endif                        // the extra resident CTAs pay more than the private columns lose (dark 3.36 -> 2.45 ms)
+constexpr int STATS_WIN = DCT_STATS_WIN;
 constexpr int STATS_ROWS = 128;               // traces per tile = threads per CTA
 constexpr int STATS_CHARGE_WIN = 1024;        // CTA-private window of the charge histogram
 constexpr int STATS_PRIV_COLS = (STATS_ROWS / 32) * STATS_WIN;                 // (warp, value) columns
