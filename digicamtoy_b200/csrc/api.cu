@@ -16,6 +16,7 @@
 #include "generate.cuh"
 #include "sweep.cuh"
 #include "grid.cuh"
+#include "tensor.cuh"
 #include "replay.cuh"
 #include "stats.cuh"
 #include "selftest.cuh"
@@ -76,6 +77,10 @@ struct dct_handle {
     double mean_pe_per_trace = 0.0;
     double mean_true_baseline = 0.0;   // baseline + NSB shift, averaged over pixels (stats window)
     double mean_baseline = 0.0;
+    // tensor-core kernel (K1t): coefficient tiles live in the arena
+    const __half* tc_coef = nullptr;
+    int tc_n_cells = 0, tc_col_shift = 0;
+    float tc_v_scale = 0.0f;
     // host-output pipeline (dct_generate_host), created lazily
     cudaStream_t s_gen = nullptr, s_copy = nullptr;
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -288,6 +293,41 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     float grid_tap_host[dct::GRID_TAPS] = {0};
     for (int m = 0; m < p.grid_n && m < dct::GRID_TAPS; ++m) grid_tap_host[m] = f_grid[m];
 
+    // K1t coefficient tiles: G[n][(f, k)] = coefficient k of tap n, phase f re-expanded in
+    // v = 2u/dx - 1  (u = a (v + 1), a = dx / 2), split into fp16 hi + lo, in the canonical K-major
+    // no-swizzle UMMA layout (dct::tc_tile_offset)
+    // four tiles: hi, lo, and both again one row further down (for cells that start on an odd column)
+    const size_t tc_tile = (size_t)dct::TC_N * dct::TC_K;
+    std::vector<uint16_t> tc_coef(4 * tc_tile, 0);
+    const bool tensor_ok = dct::tensor_supported(p);
+    if (tensor_ok) {
+        const double a1 = 0.5 * dx, a2 = a1 * a1, a3 = a2 * a1;
+        for (int n = 0; n < dct::TC_TAPS; ++n)
+            for (int f = 0; f < dct::TC_PHASES; ++f) {
+                const int m = f + dct::TC_PHASES * n;
+                if (m >= n_iv) continue;
+                const double* k = c->coef + 4 * m;
+                const double g[4] = {k[0] + k[1] * a1 + k[2] * a2 + k[3] * a3,
+                                     k[1] * a1 + 2.0 * k[2] * a2 + 3.0 * k[3] * a3,
+                                     k[2] * a2 + 3.0 * k[3] * a3, k[3] * a3};
+                for (int q = 0; q < 4; ++q) {
+                    const __half hi = __float2half_rn((float)g[q]);
+                    const __half lo = __float2half_rn((float)(g[q] - (double)__half2float(hi)));
+                    const size_t at = (size_t)dct::tc_tile_offset(n, f * 4 + q) / 2;
+                    const size_t at1 = (size_t)dct::tc_tile_offset(n + 1, f * 4 + q) / 2;
+                    memcpy(&tc_coef[at], &hi, 2);
+                    memcpy(&tc_coef[tc_tile + at], &lo, 2);
+                    memcpy(&tc_coef[2 * tc_tile + at1], &hi, 2);
+                    memcpy(&tc_coef[3 * tc_tile + at1], &lo, 2);
+                }
+            }
+        const int n_time = (int)std::ceil(((double)p.off0 + (c->t_end - c->t0)) / c->dt) + 1;
+        const int n_useful = p.B - 1 + p.n_drop - p.cell0;
+        h->tc_n_cells = std::max(0, std::min(n_time, n_useful));
+        h->tc_col_shift = p.cell0 + 1 - p.n_drop + dct::TC_COL0;
+        h->tc_v_scale = (float)(2.0 / dx);
+    }
+
     // ---- one arena
     size_t cur = 0;
     const size_t o_rate = arena_reserve<float>(cur, P), o_inv = arena_reserve<float>(cur, P),
@@ -302,7 +342,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                  o_c64 = arena_reserve<double>(cur, (size_t)n_iv * 4),
                  o_kn = arena_reserve<double>(cur, (size_t)n_iv + 1),
                  o_poly = arena_reserve<float>(cur, f_poly.size() + 4),
-                 o_grid = arena_reserve<float>(cur, f_grid.size());
+                 o_grid = arena_reserve<float>(cur, f_grid.size()),
+                 o_tc = arena_reserve<uint16_t>(cur, tc_coef.size());
     h->arena.size = cur + 256;
     cudaError_t e = cudaMalloc(&h->arena.base, h->arena.size);
     if (e != cudaSuccess) {
@@ -318,7 +359,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     UP(o_rate, f_rate); UP(o_inv, f_inv); UP(o_xt, f_xt); UP(o_exp, f_exp); UP(o_gain, f_gain);
     UP(o_s1, f_s1); UP(o_se, f_se); UP(o_base, f_base); UP(o_dgain, d_gain); UP(o_dbase, d_base);
     UP(o_npe, f_npe); UP(o_tsig, f_tsig); UP(o_jit, f_jit); UP(o_c32, f_coef); UP(o_poly, f_poly);
-    UP(o_grid, f_grid);
+    UP(o_grid, f_grid); UP(o_tc, tc_coef);
 #undef UP
     if (ue == cudaSuccess) ue = up(o_c64, c->coef, (size_t)n_iv * 4 * sizeof(double));
     if (ue == cudaSuccess) ue = up(o_kn, c->knot_x, ((size_t)n_iv + 1) * sizeof(double));
@@ -337,6 +378,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     p.coef32 = (const float4*)(base + o_c32); p.coef64 = (const double*)(base + o_c64);
     p.knots = (const double*)(base + o_kn); p.poly = (const float4*)(base + o_poly);
     p.grid_tap = (const float*)(base + o_grid);
+    h->tc_coef = (const __half*)(base + o_tc);
 
     // ---- kernel selection and launch geometry
     h->poly = p.n_phase > 0 && p.sub_binning <= 0;
@@ -371,8 +413,16 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                     "sweep kernel needs the polyphase table with %d taps, continuous NSB and <= %d bins",
                     dct::SWEEP_TAPS, dct::SWEEP_MAX_BINS);
     }
+    if (want == DCT_KERNEL_TENSOR && !(tensor_ok && h->tc_n_cells > 0)) {
+        cudaFree(h->arena.base);
+        delete h;
+        return fail(DCT_E_UNSUPPORTED,
+                    "tensor kernel needs the polyphase table with %d taps, continuous NSB and an even number of <= %d bins",
+                    dct::TC_TAPS, dct::TC_MAX_BINS);
+    }
     if (want == DCT_KERNEL_AUTO)
         want = grid_ok ? DCT_KERNEL_GRID
+             : (tensor_ok && h->tc_n_cells > 0 && h->mean_pe_per_trace >= DCT_TC_MIN_MEAN_PE) ? DCT_KERNEL_TENSOR
              : (sweep_ok && h->mean_pe_per_trace >= dct::SWEEP_MIN_MEAN_PE) ? DCT_KERNEL_SWEEP
                                                                             : DCT_KERNEL_SCATTER;
     h->kernel = want;
@@ -391,8 +441,8 @@ void dct_destroy(dct_handle* h) {
 
 int dct_selected_kernel(const dct_handle* h) { return h ? h->kernel : DCT_E_ARG; }
 
-int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
-                 float* sig_time, float* sig_charge, void* stream) {
+static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
+                         float* sig_time, float* sig_charge, float* analog, void* stream) {
     if (!h || !adc) return fail(DCT_E_ARG, "handle or adc is NULL");
     if (n_events == 0) return DCT_OK;
     if ((first_event + n_events) >> 56) return fail(DCT_E_ARG, "event index exceeds 2^56");
@@ -405,12 +455,31 @@ int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     a.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
     a.adc = adc; a.sig_time = sig_time; a.sig_charge = sig_charge;
     a.table_in_smem = h->table_in_smem ? 1 : 0;
+    a.analog = analog;
+    if (h->kernel == DCT_KERNEL_TENSOR) {
+        dct::TensorArgs ta;
+        ta.g = a;
+        ta.coef = h->tc_coef;
+        ta.n_cells = h->tc_n_cells; ta.col_shift = h->tc_col_shift; ta.v_scale = h->tc_v_scale;
+        return dct::launch_tensor(h->device, ta, st, g_err, sizeof(g_err));
+    }
     if (h->kernel == DCT_KERNEL_GRID) return dct::launch_grid(h->device, a, h->grid_tap, st, g_err, sizeof(g_err));
     if (h->kernel == DCT_KERNEL_SWEEP) return dct::launch_sweep(h->device, h->sm_count, a, st, g_err, sizeof(g_err));
     if (h->gen_threads == 32)
         return h->poly ? launch_scatter<true, 32>(h, a, st) : launch_scatter<false, 32>(h, a, st);
     return h->poly ? launch_scatter<true, dct::GEN_THREADS>(h, a, st)
                    : launch_scatter<false, dct::GEN_THREADS>(h, a, st);
+}
+
+int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
+                 float* sig_time, float* sig_charge, void* stream) {
+    return generate_impl(h, seed, first_event, n_events, adc, sig_time, sig_charge, nullptr, stream);
+}
+
+int dct_generate_analog(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
+                        float* analog, void* stream) {
+    if (!analog) return fail(DCT_E_ARG, "analog is NULL");
+    return generate_impl(h, seed, first_event, n_events, adc, nullptr, nullptr, analog, stream);
 }
 
 int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,

@@ -67,7 +67,14 @@ struct GenArgs {
     float* sig_time;
     float* sig_charge;
     int table_in_smem;          // generic coef32 table staged in shared memory
+    float* analog = nullptr;    // test hook: [n_traces, B] analog sums (p.e.-weighted template) before digitisation
 };
+
+// test hook of every generation kernel: the analog sums a trace is digitised from
+__device__ __forceinline__ void dump_analog(const GenArgs& a, uint64_t g, const float* row) {
+    if (a.analog)
+        for (int b = 0; b < a.p.B; ++b) a.analog[g * (uint64_t)a.p.B + b] = row[b];
+}
 
 // Identity of the trace a thread owns.
 struct TraceId {
@@ -397,6 +404,7 @@ k_generate_scatter(const GenArgs a) {
             }
         }
         add_signal_pulses(a, t, POLY ? p.coef32 : coef_g, row, q.xt, q.sigma1);
+        dump_analog(a, t.g, row);
         digitise_trace(p, t, row);
     }
     __syncthreads();

@@ -252,6 +252,7 @@ k_generate_sweep(const GenArgs a) {
             }
         }
         add_signal_pulses(a, t, p.coef32, row, q.xt, q.sigma1);
+        dump_analog(a, t.g, row);
         digitise_trace(p, t, row);
     }
     __syncthreads();

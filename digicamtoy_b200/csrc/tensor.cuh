@@ -1,0 +1,425 @@
+// K1t: high-rate generation kernel with the pulse shaping on the 5th-generation tensor cores.
+//
+// compute_analog_signal (reference digicamtoy/tracegenerator/__init__.py:350-362) is
+//     V[b] = sum_pe A_pe * h(t_b - t_pe),      h = cubic spline with knots every 0.5 ns.
+// Within one knot interval h is a cubic, so a pe in sampling cell c (4 ns), knot phase f (0..7),
+// local offset u contributes   A * (g0 + g1 v + g2 v^2 + g3 v^3)[tap j][phase f]   to bin c+1+j,
+// v = 2u/dx - 1 in [-1, 1].  Summing the four "moments" (A, Av, Av^2, Av^3) of all pe of one
+// (cell, phase) first turns the shaping of a cell into a small dense product
+//     D[trace, c+1+j] += M_c[trace, (f, k)] * G[(f, k), j]          (128 traces x 32 x 32)
+// with ONE constant coefficient tile G (the template is shift-invariant: cell c+1 uses the same
+// tile one accumulator column further on).  That product runs on tcgen05.mma (kind::f16, fp32
+// accumulators in TMEM); the CUDA cores are left with the random numbers, the samplers, four
+// multiplies and one 8-byte shared-memory store per pe -- no per-tap loads or FMAs, no window.
+//
+// The photo-electron stream is the one of the sweep / scatter kernels, Philox block for Philox
+// block (same advance_onset, phase_of, nsb_amplitude), so dct_trace_pe describes this kernel too;
+// only the summation differs: moments are rounded to fp16 (11 significant bits, round to nearest,
+// unbiased) before the product, the coefficients are split hi + lo (22 bits), accumulation is
+// fp32.  The analog sum differs from the fp32 kernels by ~2e-3 LSB rms at 1 GHz
+// (tests/test_tensor_gpu.py), far below the 1.25 LSB of electronic noise; signal pulses (up to
+// thousands of pe) are NOT sent through fp16: they are shaped in fp32 by the code of generate.cuh.
+//
+// CTA = 128 traces = 4 producer warps (thread = trace) + 4 helper warps (MMA issue, slot clearing).  Producers free-run through
+// time; the moments of cell c go to slot c mod R of a shared-memory ring (A operand, K-major,
+// no swizzle).  A warp publishes the smallest cell any of its lanes is still in; once all four
+// warps are past cell c the MMA warp issues its 4 MMAs (2 k-steps x hi/lo coefficients), waits for
+// them (tcgen05.commit -> mbarrier), clears the slot and releases it.  A lane that is R cells ahead
+// of the slowest trace of the CTA idles until a slot is free.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "generate.cuh"
+
+namespace dct {
+
+constexpr int TC_TRACES = 128;                 // MMA M
+constexpr int TC_THREADS = 256;                // 4 producer warps + 4 helper warps (one issues the MMAs, all
+                                               // four clear ring slots).  A multiple of 4 warps on purpose: a warp
+                                               // may only touch the TMEM lanes 32 (%warpid % 4) .., and with 5 warps
+                                               // per CTA the second CTA of an SM faulted on its first tcgen05.st
+constexpr int TC_N = 32;                       // accumulator columns per cell MMA (22 taps + padding)
+constexpr int TC_TAPS = 22;
+constexpr int TC_PHASES = 8;
+constexpr int TC_K = TC_PHASES * 4;            // fp16 K per cell: 8 phases x 4 moments
+constexpr int TC_SLOT_BYTES = TC_TRACES * TC_K * 2;      // 8 KiB
+constexpr int TC_G_BYTES = TC_N * TC_K * 2;              // 2 KiB per coefficient tile
+constexpr int TC_COL0 = 16;                    // TMEM column of kept bin 0
+constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
+#ifndef DCT_TC_RING
+#define DCT_TC_RING 8
+#endif
+#ifndef DCT_TC_MIN_BLOCKS
+#define DCT_TC_MIN_BLOCKS 2
+#endif
+// mean pe per trace from which AUTO prefers this kernel over the sweep kernel (measured crossover)
+#ifndef DCT_TC_MIN_MEAN_PE
+#define DCT_TC_MIN_MEAN_PE 40.0
+#endif
+
+struct TensorArgs {
+    GenArgs g;
+    // coefficient tiles [TC_N][TC_K] in the canonical K-major no-swizzle layout (tc_tile_offset):
+    // hi, lo, then the same two with every tap one row (= accumulator column) further down.
+    // tcgen05.mma faults ("misaligned address") on an odd accumulator column, so odd cells
+    // accumulate from the even column below through the shifted tiles.
+    const __half* coef;
+    int n_cells;                 // cells cell0 .. cell0 + n_cells - 1 can reach a kept bin
+    int col_shift;               // accumulator column of tap 0 of cell c (relative to cell0): c + col_shift
+    float v_scale;               // 2 / knot_dx
+};
+
+// Byte offset of element (row, k) in a canonical K-major, no-swizzle UMMA operand tile with
+// K = 32 halves: 8-row x 16-byte core matrices, 128 B apart along K (LBO), 512 B apart along
+// rows (SBO).
+__host__ __device__ inline int tc_tile_offset(int row, int k) {
+    return (row >> 3) * 512 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+
+inline bool tensor_supported(const DevParams& p) {
+    return p.n_phase == TC_PHASES && p.n_taps == TC_TAPS && p.sub_binning <= 0 && p.B <= TC_MAX_BINS &&
+           p.cell0 >= 0 && p.n_drop - 1 - p.cell0 <= TC_COL0 && (p.B & 1) == 0;
+}
+
+__host__ __device__ inline size_t tensor_smem_bytes(int B, int ring) {
+    size_t ringb = (size_t)ring * TC_SLOT_BYTES;
+    size_t rows = (size_t)TC_TRACES * row_stride(B) * sizeof(float);
+#ifndef DCT_TC_PAD_SMEM
+#define DCT_TC_PAD_SMEM 0      // experiment: extra bytes to limit the CTAs per SM
+#endif
+    return (ringb > rows ? ringb : rows) + 4 * TC_G_BYTES + 64 + DCT_TC_PAD_SMEM;
+}
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 in
+// [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout type 0 in [61,64))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    const uint64_t lo = (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16);
+    const uint64_t hi = (uint64_t)(512u >> 4) | (1ull << 14);
+    return lo | (hi << 32);
+}
+
+// instruction descriptor: D = F32, A = B = F16, both K-major, N = 32, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_TRACES >> 4) << 24);
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+// bounded wait: a protocol error traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// 16 consecutive accumulator columns of this warp's 32 lanes -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// zero 32 consecutive accumulator columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        :: "r"(taddr), "r"(z) : "memory");
+}
+
+}  // namespace tc
+
+template <int RING>
+__global__ void __launch_bounds__(TC_THREADS, DCT_TC_MIN_BLOCKS)
+k_generate_tensor(const TensorArgs ta) {
+    static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size must be a power of two");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GenArgs& a = ta.g;
+    const DevParams& p = a.p;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = p.B;
+
+    // ---- shared memory carve-up
+    const size_t ring_bytes = (size_t)RING * TC_SLOT_BYTES;
+    const size_t rows_bytes = (size_t)TC_TRACES * row_stride(B) * sizeof(float);
+    unsigned char* ring = smem_raw;                                   // also the float rows of the epilogue
+    unsigned char* g_tiles = smem_raw + (ring_bytes > rows_bytes ? ring_bytes : rows_bytes);   // hi, lo, hi', lo'
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(g_tiles + 4 * TC_G_BYTES);
+    // ctl[0..3]: cell every lane of producer warp w has reached; ctl[4]: cells released by the MMA
+    // warp; ctl[5]: TMEM base; ctl[8..9]: mbarrier the MMAs commit to
+    uint32_t* warp_pos = ctl;
+    uint32_t* released = ctl + 4;
+    uint32_t* tmem_slot = ctl + 5;
+    const uint32_t bar = tc::smem_u32(ctl + 8);
+
+    // ---- one-time setup
+    {
+        const int4* src = reinterpret_cast<const int4*>(ta.coef);
+        for (int i = tid; i < 4 * TC_G_BYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(g_tiles)[i] = src[i];
+        int4* r4 = reinterpret_cast<int4*>(ring);
+        for (int i = tid; i < (int)(ring_bytes / 16); i += TC_THREADS) r4[i] = make_int4(0, 0, 0, 0);
+        if (tid < 5) ctl[tid] = 0;          // not ctl[5]: tcgen05.alloc (warp 4) writes it concurrently
+        if (tid == 0) {
+            tc::mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(tc::smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_async_proxy();           // zeroed ring + coefficient tiles -> visible to the tensor core
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = tc::ld_volatile(tmem_slot);
+    const int n_cells = ta.n_cells;
+
+    if (warp < 4) {
+        // clear this warp's 32 accumulator lanes
+        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < TC_TMEM_COLS; c += 32) tc::tmem_zero32(tw + c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+
+    const uint64_t trace0 = (uint64_t)blockIdx.x * TC_TRACES;
+
+    if (warp >= 4) {
+        // ================= helper warps: warp 4 issues the MMAs, all four clear consumed slots
+        const uint32_t ring_addr = tc::smem_u32(ring);
+        const uint32_t g_addr = tc::smem_u32(g_tiles);
+        for (int c = 0; c < n_cells; ++c) {
+            const uint32_t slot = ring_addr + (uint32_t)(c & (RING - 1)) * TC_SLOT_BYTES;
+            if (warp == 4) {
+                // wait until every producer warp is past cell c
+                const long long t0 = clock64();
+                while (true) {
+                    const uint32_t m = min(min(tc::ld_volatile(warp_pos), tc::ld_volatile(warp_pos + 1)),
+                                           min(tc::ld_volatile(warp_pos + 2), tc::ld_volatile(warp_pos + 3)));
+                    if (m > (uint32_t)c) break;
+                    __nanosleep(64);
+                    if (clock64() - t0 > 4000000000ll) __trap();
+                }
+                __threadfence_block();
+                tc::fence_after();
+                if (lane == 0) {
+                    const uint32_t col = (uint32_t)(c + ta.col_shift);
+                    const uint32_t d = tmem + (col & ~1u);
+                    const uint32_t g = g_addr + (col & 1u) * (2 * TC_G_BYTES);      // odd column: shifted tiles
+                    const uint64_t a0 = tc::smem_desc(slot), a1 = tc::smem_desc(slot + 256);
+                    tc::mma_f16(d, a0, tc::smem_desc(g), 1u);
+                    tc::mma_f16(d, a1, tc::smem_desc(g + 256), 1u);
+                    tc::mma_f16(d, a0, tc::smem_desc(g + TC_G_BYTES), 1u);
+                    tc::mma_f16(d, a1, tc::smem_desc(g + TC_G_BYTES + 256), 1u);
+                    tc::mma_commit(bar);
+                }
+                __syncwarp();
+            }
+            tc::mbar_wait(bar, (uint32_t)(c & 1));
+            if (c + RING < n_cells) {
+                // the slot will be used again: clear it (generic writes after the async reads finished)
+                int4* s4 = reinterpret_cast<int4*>(ring + (size_t)(c & (RING - 1)) * TC_SLOT_BYTES);
+                const int h = tid - 128;                       // 128 helper threads x 4 x 16 B = 8 KiB
+#pragma unroll
+                for (int i = 0; i < TC_SLOT_BYTES / 16 / 128; ++i) s4[i * 128 + h] = make_int4(0, 0, 0, 0);
+                tc::fence_async_proxy();
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");     // all helpers: slot cleared
+            if (tid == 128) tc::st_volatile(released, (uint32_t)(c + 1));
+        }
+    } else {
+        // ================= producer warps: thread = trace
+        const bool live = trace0 + tid < a.n_traces;
+        TraceId t = trace_id(a, live ? trace0 + tid : 0);
+        const float rate = live ? p.rate[t.pixel] : 0.0f;
+        const PixelNsb q = load_pixel_nsb(p, t.pixel);
+        // row offset of this trace inside a slot (K-major core matrices, see tc_tile_offset)
+        const uint32_t row_off = tc::smem_u32(ring) + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
+
+        float elapsed = 0.0f;
+        int cell = p.cell0;
+        float off = p.off0;
+        bool fin = !(rate > 0.0f);
+        bool have = false;
+        uint32_t pos = fin ? (uint32_t)n_cells : 0u;     // cell (relative to cell0) this lane is in
+        uint32_t warp_done = 0;
+        int last_key = -1;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        float A = 0.f, u = 0.f;
+        int f = 0;
+        uint32_t i = 0;
+        u32x4 r = draw_block(t.key, STREAM_NSB, 0u);
+        long long spin_t0 = clock64();
+
+        while (true) {
+            if (!have && !fin) {
+                const u32x4 rn = draw_block(t.key, STREAM_NSB, i + 1u);   // independent of r: overlaps
+                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
+                elapsed += gap;
+                if (elapsed >= p.span) {
+                    fin = true;
+                    pos = (uint32_t)n_cells;
+                } else {
+                    advance_onset(p, gap, cell, off);
+                    const int c = cell - p.cell0;
+                    if (c >= n_cells) {                    // beyond the last cell that reaches a kept bin
+                        fin = true;
+                        pos = (uint32_t)n_cells;
+                    } else {
+                        A = nsb_amplitude(r, q);
+                        phase_of(p, p.dt - off, f, u);
+                        pos = (uint32_t)c;
+                        have = true;
+                    }
+                }
+                r = rn;
+                ++i;
+            }
+            // publish the cell every lane of this warp has reached
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, pos);
+            if (wmin > warp_done) {
+                tc::fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) tc::st_volatile(warp_pos + warp, wmin);
+                warp_done = wmin;
+            }
+            if (wmin >= (uint32_t)n_cells) break;
+            const uint32_t freed = tc::ld_volatile(released);
+            const bool go = have && pos < freed + (uint32_t)RING;
+            if (go) {
+                const int key = (int)(pos << 3) | f;
+                const float keep = key == last_key ? 1.0f : 0.0f;
+                last_key = key;
+                const float v = __fmaf_rn(u, ta.v_scale, -1.0f);
+                const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
+                acc0 = __fmaf_rn(acc0, keep, A);
+                acc1 = __fmaf_rn(acc1, keep, m1);
+                acc2 = __fmaf_rn(acc2, keep, m2);
+                acc3 = __fmaf_rn(acc3, keep, m3);
+                const __half2 h01 = __floats2half2_rn(acc0, acc1);
+                const __half2 h23 = __floats2half2_rn(acc2, acc3);
+                const uint32_t addr = row_off + (pos & (uint32_t)(RING - 1)) * TC_SLOT_BYTES +
+                                      (uint32_t)((f >> 1) * 128 + (f & 1) * 8);
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
+                             :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                                "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+                have = false;
+            }
+            if (__any_sync(0xffffffffu, go || (!have && !fin))) {
+                spin_t0 = clock64();
+            } else {
+                __nanosleep(32);
+                if (clock64() - spin_t0 > 4000000000ll) __trap();
+            }
+        }
+        // every MMA of this CTA has completed once the last cell is released
+        {
+            const long long t0 = clock64();
+            while (tc::ld_volatile(released) < (uint32_t)n_cells) {
+                __nanosleep(32);
+                if (clock64() - t0 > 4000000000ll) __trap();
+            }
+        }
+        __threadfence_block();
+        tc::fence_after();
+    }
+    // the ring is dead from here on: it becomes the float rows of the epilogue
+    __syncthreads();
+
+    if (warp < 4) {
+        float* rows = reinterpret_cast<float*>(smem_raw);
+        float* row = rows + tid * row_stride(B);
+        const bool live = trace0 + tid < a.n_traces;
+        for (int b = 0; b < B; ++b) row[b] = 0.0f;
+        if (live) {
+            const TraceId t = trace_id(a, trace0 + tid);
+            add_signal_pulses(a, t, p.coef32, row, p.xt[t.pixel], p.sigma1[t.pixel]);
+        }
+        // NSB sums: accumulator columns TC_COL0 .. TC_COL0 + B - 1 of this thread's TMEM lane
+        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + TC_COL0;
+        for (int b0 = 0; b0 < B; b0 += 16) {
+            float d[16];
+            tc::tmem_ld16(tw + b0, d);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (b0 + j < B) row[b0 + j] += d[j];
+        }
+        tc::fence_before();
+        if (live) {
+            const TraceId t = trace_id(a, trace0 + tid);
+            dump_analog(a, t.g, row);
+            digitise_trace(p, t, row);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        store_run<TC_TRACES>(a, trace0, rows);
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc::fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+inline int launch_tensor(int device, const TensorArgs& ta, cudaStream_t st, char* err, size_t err_len) {
+    auto kern = k_generate_tensor<DCT_TC_RING>;
+    const size_t smem = tensor_smem_bytes(ta.g.p.B, DCT_TC_RING);
+    static thread_local size_t configured[16] = {0};
+    if (configured[device & 15] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { snprintf(err, err_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+        configured[device & 15] = smem;
+    }
+    const uint64_t blocks = (ta.g.n_traces + TC_TRACES - 1) / TC_TRACES;
+    if (blocks > 0x7fffffffull) { snprintf(err, err_len, "too many traces for one launch"); return -1; }
+    kern<<<(unsigned)blocks, TC_THREADS, smem, st>>>(ta);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, err_len, "tensor launch failed: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+}  // namespace dct

@@ -18,12 +18,13 @@ LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
 CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
 
 DCT_ABI_VERSION = 1
-KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP, KERNEL_GRID = 0, 1, 2, 3
-KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep', KERNEL_GRID: 'grid'}
+KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP, KERNEL_GRID, KERNEL_TENSOR = 0, 1, 2, 3, 4
+KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep', KERNEL_GRID: 'grid',
+                KERNEL_TENSOR: 'tensor'}
 
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',
-    'dct_generate', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
+    'dct_generate', 'dct_generate_analog', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
     'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe',
 )
 
@@ -79,6 +80,7 @@ def load_library():
     lib.dct_selected_kernel.argtypes = [vp]
     lib.dct_generate.argtypes = [vp, u64, u64, u32, vp, vp, vp, vp]
     lib.dct_generate_host.argtypes = [vp, u64, u64, u32, vp, vp, vp]
+    lib.dct_generate_analog.argtypes = [vp, u64, u64, u32, vp, vp, vp]
     for f in (lib.dct_replay_f64, lib.dct_replay_f32):
         f.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dct_stats_accumulate.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
@@ -149,6 +151,9 @@ class Handle:
                  stream=None):
         check(self.lib.dct_generate(self.ptr, seed, first_event, n_events, adc_ptr, sig_time_ptr,
                                     sig_charge_ptr, stream))
+
+    def generate_analog(self, seed, first_event, n_events, adc_ptr, analog_ptr, stream=None):
+        check(self.lib.dct_generate_analog(self.ptr, seed, first_event, n_events, adc_ptr, analog_ptr, stream))
 
     def generate_host(self, seed, first_event, n_events, adc_ptr, sig_time_ptr=None,
                       sig_charge_ptr=None):

@@ -25,7 +25,7 @@ from . import native
 from .params import ARTIFICIAL_BACKWARD_TIME, build_params, evaluate_template, resolve_pulse_shape_file
 
 _KERNELS = {'auto': native.KERNEL_AUTO, 'scatter': native.KERNEL_SCATTER, 'sweep': native.KERNEL_SWEEP,
-            'grid': native.KERNEL_GRID}
+            'grid': native.KERNEL_GRID, 'tensor': native.KERNEL_TENSOR}
 
 
 def _torch():
@@ -222,6 +222,19 @@ class NTraceGenerator:
                                   t.data_ptr() if truth else None, q.data_ptr() if truth else None,
                                   stream)
         return (out, t, q) if truth else out
+
+    def generate_analog(self, n_events, first_event=0):
+        """Test hook: ``(adc int16 [n,P,B], analog float32 [n,P,B])`` CUDA tensors, ``analog`` being the
+        p.e.-weighted template sums each sample is digitised from (before gain, noise, baseline)."""
+        torch = _torch()
+        p = self.params
+        dev = torch.device('cuda', self.device)
+        adc = torch.empty((int(n_events), p.n_pixels, p.n_bins), dtype=torch.int16, device=dev)
+        analog = torch.empty((int(n_events), p.n_pixels, p.n_bins), dtype=torch.float32, device=dev)
+        if n_events:
+            self._handle.generate_analog(self.seed, int(first_event), int(n_events), adc.data_ptr(),
+                                         analog.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return adc, analog
 
     def generate_host(self, n_events, first_event=None, out=None, truth=True):
         """Same, into pinned host memory through the library's chunked D2H pipeline; returns

@@ -43,14 +43,16 @@ enum {
     DCT_E_NOMEM = -4
 };
 
-/* Kernel selection for dct_generate.  DCT_KERNEL_AUTO: the sweep kernel whenever the configuration
- * supports it (22-tap / 8-phase polyphase table, continuous NSB), the grid kernel for sub_binning > 0
- * (at most 24 on-grid template taps), else the scatter kernel. */
+/* Kernel selection for dct_generate.  DCT_KERNEL_AUTO: the grid kernel for sub_binning > 0 (at most
+ * 24 on-grid template taps); else, for the 22-tap / 8-phase polyphase table with continuous NSB, the
+ * tensor kernel at high NSB rates and the sweep kernel below; else the scatter kernel. */
 enum {
     DCT_KERNEL_AUTO = 0,
     DCT_KERNEL_SCATTER = 1,  /* shared-memory accumulators, any template / sampling           */
     DCT_KERNEL_SWEEP = 2,    /* time-ordered register window (default template at 4 ns sampling) */
-    DCT_KERNEL_GRID = 3      /* sub_binning > 0 only: fixed on-grid taps, register window          */
+    DCT_KERNEL_GRID = 3,     /* sub_binning > 0 only: fixed on-grid taps, register window          */
+    DCT_KERNEL_TENSOR = 4    /* high NSB rates: per-cell pe moments x coefficient tile on tcgen05.mma
+                                (default template at 4 ns sampling, even n_bins <= 80)              */
 };
 
 /* Everything NTraceGenerator.__init__ derives (reference :52-157), already transformed on the
@@ -97,7 +99,7 @@ DCT_API const char* dct_last_error(void);
 DCT_API int  dct_create(const dct_config* cfg, int device, dct_handle** out);
 DCT_API void dct_destroy(dct_handle* h);
 
-/* Which kernel dct_generate will use for this config (DCT_KERNEL_SCATTER / _SWEEP / _GRID). */
+/* Which kernel dct_generate will use for this config (DCT_KERNEL_SCATTER / _SWEEP / _GRID / _TENSOR). */
 DCT_API int dct_selected_kernel(const dct_handle* h);
 
 /* replaces n_events calls of NTraceGenerator.next() (:201-226 -> stages :228-381) for global
@@ -108,6 +110,13 @@ DCT_API int dct_selected_kernel(const dct_handle* h);
  *   stream     cudaStream_t passed as void* (NULL = default stream)                            */
 DCT_API int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
                  int16_t* adc, float* sig_time, float* sig_charge, void* stream);
+
+/* Test hook (not on the product path): dct_generate that also writes the analog sums every sample
+ * is digitised from -- sum over pe of amplitude x template, in p.e., before gain / noise / baseline
+ * (the quantity of compute_analog_signal :350-362 divided by the gain).
+ *   analog     device float [n_events, P, B]                                                   */
+DCT_API int dct_generate_analog(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
+                        int16_t* adc, float* analog, void* stream);
 
 /* Same, into HOST buffers (pageable or pinned): generates in chunks on an internal stream pair and
  * overlaps the device->host copy of one chunk with the generation of the next.  Synchronous. */
