@@ -53,9 +53,11 @@ constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #ifndef DCT_TC_MIN_BLOCKS
 #define DCT_TC_MIN_BLOCKS 2
 #endif
-// mean pe per trace from which AUTO prefers this kernel over the sweep kernel (measured crossover)
+// mean pe per trace from which AUTO prefers this kernel over the sweep kernel.  1e30 = never:
+// measured on C4 (245 pe / trace) the first version needs 84 ms per 16384 events against the
+// sweep kernel's 60 ms (profiles/r02/tensor_v1.txt), so it is opt-in (kernel='tensor') for now.
 #ifndef DCT_TC_MIN_MEAN_PE
-#define DCT_TC_MIN_MEAN_PE 40.0
+#define DCT_TC_MIN_MEAN_PE 1e30
 #endif
 
 struct TensorArgs {
