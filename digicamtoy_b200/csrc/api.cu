@@ -81,6 +81,7 @@ struct dct_handle {
     const __half* tc_coef = nullptr;
     int tc_n_cells = 0, tc_col_shift = 0;
     float tc_v_scale = 0.0f;
+    int tc_check_span = 1;
     // host-output pipeline (dct_generate_host), created lazily
     cudaStream_t s_gen = nullptr, s_copy = nullptr;
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -326,6 +327,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         h->tc_n_cells = std::max(0, std::min(n_time, n_useful));
         h->tc_col_shift = p.cell0 + 1 - p.n_drop + dct::TC_COL0;
         h->tc_v_scale = (float)(2.0 / dx);
+        // the cell test ends the pe stream by itself when the useful cells end a cell before the window
+        h->tc_check_span = ((double)n_useful + 1.0) * c->dt <= (double)p.off0 + (c->t_end - c->t0) ? 0 : 1;
     }
 
     // ---- one arena
@@ -461,6 +464,11 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
         ta.g = a;
         ta.coef = h->tc_coef;
         ta.n_cells = h->tc_n_cells; ta.col_shift = h->tc_col_shift; ta.v_scale = h->tc_v_scale;
+        ta.check_span = h->tc_check_span;
+        for (int r = 0; r < DCT_PHILOX_ROUNDS; ++r) {
+            ta.rk[2 * r] = a.k0 + (uint32_t)r * 0x9E3779B9u;
+            ta.rk[2 * r + 1] = a.k1 + (uint32_t)r * 0xBB67AE85u;
+        }
         return dct::launch_tensor(h->device, ta, st, g_err, sizeof(g_err));
     }
     if (h->kernel == DCT_KERNEL_GRID) return dct::launch_grid(h->device, a, h->grid_tap, st, g_err, sizeof(g_err));

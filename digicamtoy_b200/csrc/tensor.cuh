@@ -48,10 +48,13 @@ constexpr int TC_COL0 = 16;                    // TMEM column of kept bin 0
 constexpr int TC_TMEM_COLS = 128;
 constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #ifndef DCT_TC_RING
-#define DCT_TC_RING 8
+#define DCT_TC_RING 5                          // 40 KiB of moment slots: four CTAs (all 512 TMEM columns) per SM
 #endif
 #ifndef DCT_TC_MIN_BLOCKS
-#define DCT_TC_MIN_BLOCKS 2
+#define DCT_TC_MIN_BLOCKS 4
+#endif
+#ifndef DCT_TC_UNROLL
+#define DCT_TC_UNROLL 2                        // photo-electrons per lane between two looks at the ring state
 #endif
 // mean pe per trace from which AUTO prefers this kernel over the sweep kernel.  1e30 = never:
 // measured on C4 (245 pe / trace) the first version needs 84 ms per 16384 events against the
@@ -70,6 +73,8 @@ struct TensorArgs {
     int n_cells;                 // cells cell0 .. cell0 + n_cells - 1 can reach a kept bin
     int col_shift;               // accumulator column of tap 0 of cell c (relative to cell0): c + col_shift
     float v_scale;               // 2 / knot_dx
+    int check_span;              // 0: the cell test alone ends the pe stream (see k_generate_tensor)
+    uint32_t rk[2 * DCT_PHILOX_ROUNDS];   // Philox round keys of the seed: (k0 + r W0, k1 + r W1), r = 0 .. ROUNDS-1
 };
 
 // Byte offset of element (row, k) in a canonical K-major, no-swizzle UMMA operand tile with
@@ -170,10 +175,36 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
 
 }  // namespace tc
 
-template <int RING>
+// Philox4x32 with the round keys as kernel parameters: the key schedule (k + r W) depends only on
+// the seed, so the XORs take it straight from the constant bank -- no key registers, no adds.
+// Bit-identical to draw_block(key, STREAM_NSB, block).
+__device__ __forceinline__ u32x4 philox_rk(uint32_t block, uint32_t cy, uint32_t cz, uint32_t cw,
+                                           const uint32_t (&rk)[2 * DCT_PHILOX_ROUNDS]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    u32x4 c;
+    c.x = block; c.y = cy; c.z = cz; c.w = cw;
+#pragma unroll
+    for (int r = 0; r < DCT_PHILOX_ROUNDS; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c.x;
+        const uint64_t p1 = (uint64_t)M1 * c.z;
+        u32x4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk[2 * r];
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk[2 * r + 1];
+        n.w = (uint32_t)p0;
+        c = n;
+    }
+    return c;
+}
+
+// CHECK_SPAN: the pe stream ends where the elapsed time passes the NSB window (as in the other
+// kernels).  When the last cell that can reach a kept bin ends a full cell before the window does
+// (C4: cells 0..58 of 60), the cell test alone ends the stream at the same pe or earlier, with
+// nothing lost, and the elapsed time need not be tracked.
+template <int RING, bool CHECK_SPAN>
 __global__ void __launch_bounds__(TC_THREADS, DCT_TC_MIN_BLOCKS)
-k_generate_tensor(const TensorArgs ta) {
-    static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size must be a power of two");
+k_generate_tensor(const __grid_constant__ TensorArgs ta) {
+    static_assert(RING >= 2, "ring needs two slots");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GenArgs& a = ta.g;
     const DevParams& p = a.p;
@@ -234,17 +265,18 @@ k_generate_tensor(const TensorArgs ta) {
         // ================= helper warps: warp 4 issues the MMAs, all four clear consumed slots
         const uint32_t ring_addr = tc::smem_u32(ring);
         const uint32_t g_addr = tc::smem_u32(g_tiles);
+        int slot_i = 0;
         for (int c = 0; c < n_cells; ++c) {
-            const uint32_t slot = ring_addr + (uint32_t)(c & (RING - 1)) * TC_SLOT_BYTES;
+            const uint32_t slot = ring_addr + (uint32_t)slot_i * TC_SLOT_BYTES;
             if (warp == 4) {
                 // wait until every producer warp is past cell c
-                const long long t0 = clock64();
+                uint32_t spins = 0;
                 while (true) {
                     const uint32_t m = min(min(tc::ld_volatile(warp_pos), tc::ld_volatile(warp_pos + 1)),
                                            min(tc::ld_volatile(warp_pos + 2), tc::ld_volatile(warp_pos + 3)));
                     if (m > (uint32_t)c) break;
-                    __nanosleep(64);
-                    if (clock64() - t0 > 4000000000ll) __trap();
+                    __nanosleep(48);
+                    if (++spins > (1u << 26)) __trap();
                 }
                 __threadfence_block();
                 tc::fence_after();
@@ -264,7 +296,7 @@ k_generate_tensor(const TensorArgs ta) {
             tc::mbar_wait(bar, (uint32_t)(c & 1));
             if (c + RING < n_cells) {
                 // the slot will be used again: clear it (generic writes after the async reads finished)
-                int4* s4 = reinterpret_cast<int4*>(ring + (size_t)(c & (RING - 1)) * TC_SLOT_BYTES);
+                int4* s4 = reinterpret_cast<int4*>(ring + (size_t)slot_i * TC_SLOT_BYTES);
                 const int h = tid - 128;                       // 128 helper threads x 4 x 16 B = 8 KiB
 #pragma unroll
                 for (int i = 0; i < TC_SLOT_BYTES / 16 / 128; ++i) s4[i * 128 + h] = make_int4(0, 0, 0, 0);
@@ -272,15 +304,17 @@ k_generate_tensor(const TensorArgs ta) {
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");     // all helpers: slot cleared
             if (tid == 128) tc::st_volatile(released, (uint32_t)(c + 1));
+            if (++slot_i == RING) slot_i = 0;
         }
     } else {
         // ================= producer warps: thread = trace
         const bool live = trace0 + tid < a.n_traces;
-        TraceId t = trace_id(a, live ? trace0 + tid : 0);
+        const TraceId t = trace_id(a, live ? trace0 + tid : 0);
         const float rate = live ? p.rate[t.pixel] : 0.0f;
         const PixelNsb q = load_pixel_nsb(p, t.pixel);
         // row offset of this trace inside a slot (K-major core matrices, see tc_tile_offset)
         const uint32_t row_off = tc::smem_u32(ring) + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
+        const uint32_t cy = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu), cz = t.key.pixel, cw = t.key.ev_lo;
 
         float elapsed = 0.0f;
         int cell = p.cell0;
@@ -289,37 +323,61 @@ k_generate_tensor(const TensorArgs ta) {
         bool have = false;
         uint32_t pos = fin ? (uint32_t)n_cells : 0u;     // cell (relative to cell0) this lane is in
         uint32_t warp_done = 0;
-        int last_key = -1;
+        uint32_t limit = (uint32_t)RING;                 // cells below it may be written: released + RING
+        uint32_t last_key = 0xffffffffu;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        float A = 0.f, u = 0.f;
-        int f = 0;
+        float A = 0.f, v = 0.f;
+        uint32_t f = 0;
         uint32_t i = 0;
-        u32x4 r = draw_block(t.key, STREAM_NSB, 0u);
-        long long spin_t0 = clock64();
+        uint32_t idle = 0;
+        u32x4 r = philox_rk(0u, cy, cz, cw, ta.rk);
 
         while (true) {
-            if (!have && !fin) {
-                const u32x4 rn = draw_block(t.key, STREAM_NSB, i + 1u);   // independent of r: overlaps
-                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                elapsed += gap;
-                if (elapsed >= p.span) {
-                    fin = true;
-                    pos = (uint32_t)n_cells;
-                } else {
+            bool progress = false;
+#pragma unroll
+            for (int rep = 0; rep < DCT_TC_UNROLL; ++rep) {
+                if (!have && !fin) {
+                    const u32x4 rn = philox_rk(i + 1u, cy, cz, cw, ta.rk);    // independent of r: overlaps
+                    const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
+                    bool end = false;
+                    if (CHECK_SPAN) {
+                        elapsed += gap;
+                        end = elapsed >= p.span;
+                    }
                     advance_onset(p, gap, cell, off);
                     const int c = cell - p.cell0;
-                    if (c >= n_cells) {                    // beyond the last cell that reaches a kept bin
-                        fin = true;
-                        pos = (uint32_t)n_cells;
-                    } else {
-                        A = nsb_amplitude(r, q);
-                        phase_of(p, p.dt - off, f, u);
-                        pos = (uint32_t)c;
-                        have = true;
-                    }
+                    end = end || c >= n_cells;               // beyond the last cell that reaches a kept bin
+                    A = nsb_amplitude(r, q);
+                    int fi; float u;
+                    phase_of(p, p.dt - off, fi, u);
+                    f = (uint32_t)fi;
+                    v = __fmaf_rn(u, ta.v_scale, -1.0f);
+                    pos = end ? (uint32_t)n_cells : (uint32_t)c;
+                    fin = end;
+                    have = !end;
+                    r = rn;
+                    ++i;
+                    progress = true;
                 }
-                r = rn;
-                ++i;
+                if (have && pos < limit) {
+                    const uint32_t key = (pos << 3) | f;
+                    const float keep = key == last_key ? 1.0f : 0.0f;
+                    last_key = key;
+                    const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
+                    acc0 = __fmaf_rn(acc0, keep, A);
+                    acc1 = __fmaf_rn(acc1, keep, m1);
+                    acc2 = __fmaf_rn(acc2, keep, m2);
+                    acc3 = __fmaf_rn(acc3, keep, m3);
+                    const __half2 h01 = __floats2half2_rn(acc0, acc1);
+                    const __half2 h23 = __floats2half2_rn(acc2, acc3);
+                    const uint32_t addr = row_off + (pos % (uint32_t)RING) * TC_SLOT_BYTES +
+                                          ((f >> 1) * 128u + (f & 1u) * 8u);
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
+                                 :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                                    "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+                    have = false;
+                    progress = true;
+                }
             }
             // publish the cell every lane of this warp has reached
             const uint32_t wmin = __reduce_min_sync(0xffffffffu, pos);
@@ -330,40 +388,18 @@ k_generate_tensor(const TensorArgs ta) {
                 warp_done = wmin;
             }
             if (wmin >= (uint32_t)n_cells) break;
-            const uint32_t freed = tc::ld_volatile(released);
-            const bool go = have && pos < freed + (uint32_t)RING;
-            if (go) {
-                const int key = (int)(pos << 3) | f;
-                const float keep = key == last_key ? 1.0f : 0.0f;
-                last_key = key;
-                const float v = __fmaf_rn(u, ta.v_scale, -1.0f);
-                const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
-                acc0 = __fmaf_rn(acc0, keep, A);
-                acc1 = __fmaf_rn(acc1, keep, m1);
-                acc2 = __fmaf_rn(acc2, keep, m2);
-                acc3 = __fmaf_rn(acc3, keep, m3);
-                const __half2 h01 = __floats2half2_rn(acc0, acc1);
-                const __half2 h23 = __floats2half2_rn(acc2, acc3);
-                const uint32_t addr = row_off + (pos & (uint32_t)(RING - 1)) * TC_SLOT_BYTES +
-                                      (uint32_t)((f >> 1) * 128 + (f & 1) * 8);
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
-                             :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                                "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
-                have = false;
-            }
-            if (__any_sync(0xffffffffu, go || (!have && !fin))) {
-                spin_t0 = clock64();
-            } else {
+            limit = tc::ld_volatile(released) + (uint32_t)RING;
+            if (!__any_sync(0xffffffffu, progress)) {
                 __nanosleep(32);
-                if (clock64() - spin_t0 > 4000000000ll) __trap();
+                if (++idle > (1u << 26)) __trap();       // a protocol error fails the launch instead of hanging
             }
         }
         // every MMA of this CTA has completed once the last cell is released
         {
-            const long long t0 = clock64();
+            uint32_t spins = 0;
             while (tc::ld_volatile(released) < (uint32_t)n_cells) {
                 __nanosleep(32);
-                if (clock64() - t0 > 4000000000ll) __trap();
+                if (++spins > (1u << 26)) __trap();
             }
         }
         __threadfence_block();
@@ -408,13 +444,13 @@ k_generate_tensor(const TensorArgs ta) {
 }
 
 inline int launch_tensor(int device, const TensorArgs& ta, cudaStream_t st, char* err, size_t err_len) {
-    auto kern = k_generate_tensor<DCT_TC_RING>;
+    auto kern = ta.check_span ? k_generate_tensor<DCT_TC_RING, true> : k_generate_tensor<DCT_TC_RING, false>;
     const size_t smem = tensor_smem_bytes(ta.g.p.B, DCT_TC_RING);
-    static thread_local size_t configured[16] = {0};
-    if (configured[device & 15] < smem) {
+    static thread_local size_t configured[16][2] = {{0}};
+    if (configured[device & 15][ta.check_span] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { snprintf(err, err_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
-        configured[device & 15] = smem;
+        configured[device & 15][ta.check_span] = smem;
     }
     const uint64_t blocks = (ta.g.n_traces + TC_TRACES - 1) / TC_TRACES;
     if (blocks > 0x7fffffffull) { snprintf(err, err_len, "too many traces for one launch"); return -1; }
