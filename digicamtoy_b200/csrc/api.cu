@@ -82,6 +82,7 @@ struct dct_handle {
     int tc_n_cells = 0, tc_col_shift = 0;
     float tc_v_scale = 0.0f;
     int tc_check_span = 1;
+    float tc_y0 = 0.0f, tc_y_end = 0.0f;
     // host-output pipeline (dct_generate_host), created lazily
     cudaStream_t s_gen = nullptr, s_copy = nullptr;
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -314,8 +315,10 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                 for (int q = 0; q < 4; ++q) {
                     const __half hi = __float2half_rn((float)g[q]);
                     const __half lo = __float2half_rn((float)(g[q] - (double)__half2float(hi)));
-                    const size_t at = (size_t)dct::tc_tile_offset(n, f * 4 + q) / 2;
-                    const size_t at1 = (size_t)dct::tc_tile_offset(n + 1, f * 4 + q) / 2;
+                    // K index by j = 7 - f, the knot interval within the cell in time order (see tensor.cuh)
+                    const int kk = (dct::TC_PHASES - 1 - f) * 4 + q;
+                    const size_t at = (size_t)dct::tc_tile_offset(n, kk) / 2;
+                    const size_t at1 = (size_t)dct::tc_tile_offset(n + 1, kk) / 2;
                     memcpy(&tc_coef[at], &hi, 2);
                     memcpy(&tc_coef[tc_tile + at], &lo, 2);
                     memcpy(&tc_coef[2 * tc_tile + at1], &hi, 2);
@@ -329,6 +332,11 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         h->tc_v_scale = (float)(2.0 / dx);
         // the cell test ends the pe stream by itself when the useful cells end a cell before the window
         h->tc_check_span = ((double)n_useful + 1.0) * c->dt <= (double)p.off0 + (c->t_end - c->t0) ? 0 : 1;
+        // producer clock in knot steps from the start of cell0; the stream ends at the end of the
+        // NSB window or after the last useful cell, whichever comes first
+        h->tc_y0 = (float)((double)p.off0 / dx);
+        h->tc_y_end = (float)std::min(((double)p.off0 + (c->t_end - c->t0)) / dx,
+                                      (double)h->tc_n_cells * dct::TC_PHASES);
     }
 
     // ---- one arena
@@ -465,6 +473,7 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
         ta.coef = h->tc_coef;
         ta.n_cells = h->tc_n_cells; ta.col_shift = h->tc_col_shift; ta.v_scale = h->tc_v_scale;
         ta.check_span = h->tc_check_span;
+        ta.y0 = h->tc_y0; ta.y_end = h->tc_y_end;
         for (int r = 0; r < DCT_PHILOX_ROUNDS; ++r) {
             ta.rk[2 * r] = a.k0 + (uint32_t)r * 0x9E3779B9u;
             ta.rk[2 * r + 1] = a.k1 + (uint32_t)r * 0xBB67AE85u;

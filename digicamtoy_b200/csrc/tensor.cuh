@@ -53,6 +53,9 @@ constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #ifndef DCT_TC_MIN_BLOCKS
 #define DCT_TC_MIN_BLOCKS 4
 #endif
+#ifndef DCT_TC_POLL_NS
+#define DCT_TC_POLL_NS 200                     // sleep of the MMA warp between two looks at the producers' positions
+#endif
 #ifndef DCT_TC_UNROLL
 #define DCT_TC_UNROLL 2                        // photo-electrons per lane between two looks at the ring state
 #endif
@@ -74,6 +77,7 @@ struct TensorArgs {
     int col_shift;               // accumulator column of tap 0 of cell c (relative to cell0): c + col_shift
     float v_scale;               // 2 / knot_dx
     int check_span;              // 0: the cell test alone ends the pe stream (see k_generate_tensor)
+    float y0, y_end;             // producer clock in knot steps from the start of cell0: first value, end of the stream
     uint32_t rk[2 * DCT_PHILOX_ROUNDS];   // Philox round keys of the seed: (k0 + r W0, k1 + r W1), r = 0 .. ROUNDS-1
 };
 
@@ -139,6 +143,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) break;
+        __nanosleep(32);
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
@@ -201,6 +206,15 @@ __device__ __forceinline__ u32x4 philox_rk(uint32_t block, uint32_t cy, uint32_t
 // kernels).  When the last cell that can reach a kept bin ends a full cell before the window does
 // (C4: cells 0..58 of 60), the cell test alone ends the stream at the same pe or earlier, with
 // nothing lost, and the elapsed time need not be tracked.
+// Borel cluster size as a float; same value as borel(): the first threshold inline, the rest
+// (0.8 % of the draws at xt = 0.08) through the generic sampler.
+__device__ __forceinline__ float borel_f(uint32_t r, float mu, const float4 cdf) {
+    const float u = u01_open1(r);
+    float fn = u >= cdf.x ? 2.0f : 1.0f;
+    if (u >= cdf.y) fn = (float)borel(r, mu, cdf);
+    return fn;
+}
+
 template <int RING, bool CHECK_SPAN>
 __global__ void __launch_bounds__(TC_THREADS, DCT_TC_MIN_BLOCKS)
 k_generate_tensor(const __grid_constant__ TensorArgs ta) {
@@ -262,7 +276,8 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
     const uint64_t trace0 = (uint64_t)blockIdx.x * TC_TRACES;
 
     if (warp >= 4) {
-        // ================= helper warps: warp 4 issues the MMAs, all four clear consumed slots
+        // ================= helper warps: warp 4 issues the MMAs, all four clear consumed slots.
+        // Warps 5-7 only ever wait at hardware barriers (no issue slots); warp 4 polls with sleeps.
         const uint32_t ring_addr = tc::smem_u32(ring);
         const uint32_t g_addr = tc::smem_u32(g_tiles);
         int slot_i = 0;
@@ -275,8 +290,8 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     const uint32_t m = min(min(tc::ld_volatile(warp_pos), tc::ld_volatile(warp_pos + 1)),
                                            min(tc::ld_volatile(warp_pos + 2), tc::ld_volatile(warp_pos + 3)));
                     if (m > (uint32_t)c) break;
-                    __nanosleep(48);
-                    if (++spins > (1u << 26)) __trap();
+                    __nanosleep(DCT_TC_POLL_NS);
+                    if (++spins > (1u << 24)) __trap();
                 }
                 __threadfence_block();
                 tc::fence_after();
@@ -292,77 +307,75 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     tc::mma_commit(bar);
                 }
                 __syncwarp();
+                tc::mbar_wait(bar, (uint32_t)(c & 1));
             }
-            tc::mbar_wait(bar, (uint32_t)(c & 1));
             if (c + RING < n_cells) {
                 // the slot will be used again: clear it (generic writes after the async reads finished)
+                asm volatile("bar.sync 2, 128;" ::: "memory");     // MMAs of cell c done (warp 4 saw the mbarrier flip)
                 int4* s4 = reinterpret_cast<int4*>(ring + (size_t)slot_i * TC_SLOT_BYTES);
                 const int h = tid - 128;                       // 128 helper threads x 4 x 16 B = 8 KiB
 #pragma unroll
                 for (int i = 0; i < TC_SLOT_BYTES / 16 / 128; ++i) s4[i * 128 + h] = make_int4(0, 0, 0, 0);
                 tc::fence_async_proxy();
+                asm volatile("bar.sync 2, 128;" ::: "memory");     // all helpers: slot cleared
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");     // all helpers: slot cleared
             if (tid == 128) tc::st_volatile(released, (uint32_t)(c + 1));
             if (++slot_i == RING) slot_i = 0;
         }
     } else {
         // ================= producer warps: thread = trace
+        // Time runs in knot steps (0.5 ns) from the start of cell0:  y += gap / dx.  Its integer part
+        // is the knot interval (8 per cell), gi = 8 cell + j, and with w = frac(y) the pe sits
+        // x0 = (8 - j - w) dx before the next bin: phase f = 7 - j, local offset u = (1 - w) dx,
+        // v = 2u/dx - 1 = 1 - 2w.  (The sweep kernel keeps (cell, offset in ns); the two placements
+        // agree to ~1e-4 ns, a 1e-4 LSB effect.  The moments are stored by j; the coefficient tile
+        // is permuted to match.)
         const bool live = trace0 + tid < a.n_traces;
         const TraceId t = trace_id(a, live ? trace0 + tid : 0);
         const float rate = live ? p.rate[t.pixel] : 0.0f;
         const PixelNsb q = load_pixel_nsb(p, t.pixel);
+        const float gap_scale = q.neg_ln2_over_rate * p.inv_knot_dx;
         // row offset of this trace inside a slot (K-major core matrices, see tc_tile_offset)
-        const uint32_t row_off = tc::smem_u32(ring) + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
+        uint32_t row_off = tc::smem_u32(ring) + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
+        asm volatile("" : "+r"(row_off));                // keep it in a register (ptxas rebuilt it per pe)
         const uint32_t cy = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu), cz = t.key.pixel, cw = t.key.ev_lo;
+        const uint32_t n8 = (uint32_t)n_cells * TC_PHASES;
 
-        float elapsed = 0.0f;
-        int cell = p.cell0;
-        float off = p.off0;
-        bool fin = !(rate > 0.0f);
-        bool have = false;
-        uint32_t pos = fin ? (uint32_t)n_cells : 0u;     // cell (relative to cell0) this lane is in
+        // Lane state: gi = knot interval of the last pe generated (8 cell + j); pend = that pe still
+        // waits for its ring slot.  A lane whose stream has ended holds gi >= n8 with pend set for
+        // good (the write limit never exceeds n8), so "finished" needs no flag of its own.
+        float y = ta.y0;
+        uint32_t gi = (rate > 0.0f) ? 0u : n8;
+        int pend = (rate > 0.0f) ? 0 : 1;
         uint32_t warp_done = 0;
-        uint32_t limit = (uint32_t)RING;                 // cells below it may be written: released + RING
-        uint32_t last_key = 0xffffffffu;
+        uint32_t limit8 = min((uint32_t)RING * TC_PHASES, n8);   // intervals below it may be written: 8 (released + RING)
+        float keep = 0.0f;                               // 1: same (cell, interval) as the pe before -> sums carry on
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         float A = 0.f, v = 0.f;
-        uint32_t f = 0;
         uint32_t i = 0;
         uint32_t idle = 0;
         u32x4 r = philox_rk(0u, cy, cz, cw, ta.rk);
 
         while (true) {
-            bool progress = false;
 #pragma unroll
             for (int rep = 0; rep < DCT_TC_UNROLL; ++rep) {
-                if (!have && !fin) {
+                if (!pend) {
                     const u32x4 rn = philox_rk(i + 1u, cy, cz, cw, ta.rk);    // independent of r: overlaps
-                    const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                    bool end = false;
-                    if (CHECK_SPAN) {
-                        elapsed += gap;
-                        end = elapsed >= p.span;
-                    }
-                    advance_onset(p, gap, cell, off);
-                    const int c = cell - p.cell0;
-                    end = end || c >= n_cells;               // beyond the last cell that reaches a kept bin
-                    A = nsb_amplitude(r, q);
-                    int fi; float u;
-                    phase_of(p, p.dt - off, fi, u);
-                    f = (uint32_t)fi;
-                    v = __fmaf_rn(u, ta.v_scale, -1.0f);
-                    pos = end ? (uint32_t)n_cells : (uint32_t)c;
-                    fin = end;
-                    have = !end;
+                    y = fminf(__fmaf_rn(fast_lg2(u01_open0(r.x)), gap_scale, y), 4194304.0f);
+                    const float yi = __fadd_rz(y, 8388608.0f);          // 2^23 + floor(y)
+                    uint32_t g = __float_as_uint(yi) & 0x007fffffu;
+                    if (CHECK_SPAN) g = (y < ta.y_end) ? g : 0x00800000u;  // past the NSB window
+                    const float w = y - (yi - 8388608.0f);
+                    v = __fmaf_rn(w, -2.0f, 1.0f);
+                    const float fn = borel_f(r.y, q.xt, q.borel_cdf);
+                    A = __fmaf_rn(q.sigma1, normal_scaled(r.z, r.w, fn), fn);
+                    keep = g == gi ? 1.0f : 0.0f;
+                    gi = g;
+                    pend = 1;
                     r = rn;
                     ++i;
-                    progress = true;
                 }
-                if (have && pos < limit) {
-                    const uint32_t key = (pos << 3) | f;
-                    const float keep = key == last_key ? 1.0f : 0.0f;
-                    last_key = key;
+                if (pend && gi < limit8) {
                     const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
                     acc0 = __fmaf_rn(acc0, keep, A);
                     acc1 = __fmaf_rn(acc1, keep, m1);
@@ -370,26 +383,25 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     acc3 = __fmaf_rn(acc3, keep, m3);
                     const __half2 h01 = __floats2half2_rn(acc0, acc1);
                     const __half2 h23 = __floats2half2_rn(acc2, acc3);
-                    const uint32_t addr = row_off + (pos % (uint32_t)RING) * TC_SLOT_BYTES +
-                                          ((f >> 1) * 128u + (f & 1u) * 8u);
+                    const uint32_t addr = row_off + ((gi >> 3) % (uint32_t)RING) * TC_SLOT_BYTES +
+                                          (((gi & 6u) << 6) | ((gi & 1u) << 3));
                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
                                  :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
                                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
-                    have = false;
-                    progress = true;
+                    pend = 0;
                 }
             }
             // publish the cell every lane of this warp has reached
-            const uint32_t wmin = __reduce_min_sync(0xffffffffu, pos);
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, gi) >> 3;
             if (wmin > warp_done) {
                 tc::fence_async_proxy();
                 __syncwarp();
-                if (lane == 0) tc::st_volatile(warp_pos + warp, wmin);
+                if (lane == 0) tc::st_volatile(warp_pos + warp, min(wmin, (uint32_t)n_cells));
                 warp_done = wmin;
             }
             if (wmin >= (uint32_t)n_cells) break;
-            limit = tc::ld_volatile(released) + (uint32_t)RING;
-            if (!__any_sync(0xffffffffu, progress)) {
+            limit8 = min((tc::ld_volatile(released) + (uint32_t)RING) * TC_PHASES, n8);
+            if (!__any_sync(0xffffffffu, !pend || gi < limit8)) {      // every lane waits for a slot
                 __nanosleep(32);
                 if (++idle > (1u << 26)) __trap();       // a protocol error fails the launch instead of hanging
             }

@@ -1,0 +1,88 @@
+"""K1t, the tensor-core generation kernel (tcgen05.mma on per-cell pe moments): same photo-electron
+stream as the sweep kernel, pulse shaping summed through fp16 moments x (hi + lo) fp16 coefficients
+with fp32 accumulation.  Checked against the sweep kernel on the same seed, against the closed form,
+and for independence of the launch geometry."""
+import numpy as np
+import pytest
+
+from oracle import reference_port as orc
+
+pytestmark = pytest.mark.gpu
+
+ACDC = dict(time_start=0, time_end=200, time_sampling=4, crosstalk=0.08, gain_nsb=True, poisson=True,
+            sigma_e=1.25, sigma_1=0.8, gain=5, baseline=280, time_signal=20, jitter=0.2)
+
+
+def gen(**kw):
+    from digicamtoy_b200 import NTraceGenerator
+    return NTraceGenerator(**kw)
+
+
+@pytest.mark.parametrize('rate,npe,P', [(1.0, 100., 300), (0.125, 10., 131), (3.0, 0., 64), (0.01, 2., 200)])
+def test_tensor_kernel_matches_sweep_kernel_on_the_same_seed(rate, npe, P):
+    import torch
+    kw = dict(n_pixels=P, nsb_rate=rate, n_photon=npe, **ACDC)
+    gs, gt = gen(seed=7, kernel='sweep', **kw), gen(seed=7, kernel='tensor', **kw)
+    assert gs.kernel == 'sweep' and gt.kernel == 'tensor'
+    n = 40
+    adc_s, an_s = gs.generate_analog(n)
+    adc_t, an_t = gt.generate_analog(n)
+    torch.cuda.synchronize()
+    gain_eff = float(gs.gain[0])
+    d = (an_t.double() - an_s.double()).cpu().numpy() * gain_eff          # LSB
+    # fp16 rounding of the moments: random, unbiased, ~1e-3 LSB per pe
+    scale = max(1.0, np.sqrt(rate))
+    assert np.sqrt((d ** 2).mean()) < 5e-3 * scale, np.sqrt((d ** 2).mean())
+    assert abs(d.mean()) < 2e-4 * scale, d.mean()
+    # the signal pulses do not go through fp16: a 100 pe pulse leaves the difference where it was
+    dd = (adc_t.int() - adc_s.int()).cpu().numpy()
+    assert np.abs(dd).max() <= 1
+    assert (dd != 0).mean() < 5e-3 * scale
+
+
+def test_tensor_kernel_is_independent_of_chunking_and_offsets():
+    g = gen(n_pixels=37, nsb_rate=0.8, n_photon=8., seed=99, kernel='tensor', **ACDC)
+    import torch
+    def cube(n, first):
+        out = g.generate(n, first_event=first)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+    whole = cube(40, 0)
+    parts = np.concatenate([cube(7, 0), cube(13, 7), cube(20, 20)])
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(cube(5, 17), whole[17:22])
+    g2 = gen(n_pixels=37, nsb_rate=0.8, n_photon=8., seed=99, kernel='tensor', **ACDC)
+    out = g2.generate(40, first_event=0); torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), whole)
+
+
+@pytest.mark.parametrize('rate', [0.04, 1.0])
+def test_tensor_kernel_moments_against_closed_form(rate):
+    import torch
+    kw = dict(n_pixels=64, nsb_rate=rate, n_photon=0., **ACDC)
+    g = gen(seed=77, kernel='tensor', saturate=None, **kw)
+    n_events = 3000
+    c = g.generate(n_events); torch.cuda.synchronize()
+    c = c.cpu().numpy().astype(np.float64)
+    mean, var = orc.closed_form_moments(orc.make_config(**kw))
+    z = (c.mean(axis=0) - mean) / np.sqrt(var / n_events)
+    assert np.abs(z).max() < 6 and abs(z.mean()) < 6 / np.sqrt(z.size)
+    ratio = c.var(axis=0).mean(axis=0) / var.mean(axis=0)
+    assert np.abs(ratio - 1).max() < 0.03, ratio
+
+
+def test_tensor_kernel_handles_per_pixel_rates_dark_pixels_and_partial_blocks():
+    """Pixels without NSB, rates from 1 MHz to 2 GHz in one camera, a trace count that is not a
+    multiple of the 128-trace CTA, the 92-bin window falls back (more bins than accumulator columns)."""
+    import torch
+    rates = np.concatenate([np.zeros(3), np.logspace(-3, 0.3, 58)])
+    kw = dict(n_pixels=61, nsb_rate=rates, n_photon=3., **ACDC)
+    gs, gt = gen(seed=3, kernel='sweep', **kw), gen(seed=3, kernel='tensor', **kw)
+    a, b = gs.generate(33), gt.generate(33)
+    torch.cuda.synchronize()
+    d = (a.int() - b.int()).cpu().numpy()
+    assert np.abs(d).max() <= 1 and (d != 0).mean() < 5e-3
+    assert np.array_equal(a[:, :3].cpu().numpy(), b[:, :3].cpu().numpy())      # no NSB: nothing goes through fp16
+    from digicamtoy_b200 import workloads
+    with pytest.raises(ValueError):
+        gen(seed=1, kernel='tensor', **workloads.c1_dark(n_photon=1))
