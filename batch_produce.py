@@ -128,8 +128,13 @@ def parse(argv=None):
     ap.add_argument('--output_directory', default='/sst1m/MC/digicamtoy/')
     ap.add_argument('--seed', type=int, default=None, help='base seed; file (i,j,k) gets a distinct offset')
     ap.add_argument('--device', type=int, default=None)
-    ap.add_argument('--writers', type=int, default=4, help='threads that compress and write files')
-    ap.add_argument('--max_in_flight', type=int, default=6, help='files generated but not yet written')
+    ap.add_argument('--writers', type=int, default=max(1, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else 4),
+                    help='threads that compress and write files (default: one per host core of this rank)')
+    ap.add_argument('--max_in_flight', type=int, default=None,
+                    help='files generated but not yet written (default: writers + 2)')
+    ap.add_argument('--resume', action='store_true', help='skip files that already exist instead of refusing to run')
+    ap.add_argument('--compress_level', type=int, default=None,
+                    help='zlib level of the .npz bundles (default 4, what h5py uses for compression="gzip")')
     ap.add_argument('--write_configs', metavar='DIR', default=None, help='only write the YAML files there')
     ap.add_argument('--dry_run', action='store_true')
     ap.add_argument('-d', '--debug', action='store_true')
@@ -161,17 +166,27 @@ def main(argv=None):
             print(os.path.join(a.output_directory, OUTPUT_FILE_NAME.format(i, j, k)))
         return [os.path.join(a.output_directory, OUTPUT_FILE_NAME.format(i, j, k)) for i, j, k in mine]
 
-    # the reference refuses to overwrite (produce_data.py:47-57): check every file of this rank first
+    import produce_data
+    # the reference refuses to overwrite (produce_data.py:47-57): check every file of this rank first.
+    # --resume is the reference's way of finishing a production -- re-submitting the missing file ids
+    # (run.sh:19) -- in one flag: files that exist are skipped (a file only gets its name once complete).
+    todo = []
     for i, j, k in mine:
         f = os.path.join(a.output_directory, OUTPUT_FILE_NAME.format(i, j, k))
-        if os.path.exists(f) or os.path.exists(f + '.npz'):
-            log.error('File {} already exists'.format(f))
-            return 1
+        if produce_data.output_exists(f):
+            if not a.resume:
+                log.error('File {} already exists'.format(f))
+                return 1
+            continue
+        todo.append((i, j, k))
+    if a.resume:
+        log.info('rank %d: %d of %d files already there, %d to do', rank, len(mine) - len(todo), len(mine), len(todo))
+    mine = todo
     os.makedirs(a.output_directory, exist_ok=True)
-
-    import produce_data
+    if a.compress_level is not None:
+        produce_data.COMPRESS_LEVEL = a.compress_level
     n_dc, n_ids = len(nsb_rates), a.file_id[1] + 1
-    slots = threading.Semaphore(max(1, a.max_in_flight))
+    slots = threading.Semaphore(max(1, a.max_in_flight if a.max_in_flight is not None else a.writers + 2))
     pool = ThreadPoolExecutor(max_workers=max(1, a.writers))
     futures = []
 

@@ -6,7 +6,7 @@
 Workload (N=1): BASELINE.json config C4 -- full camera, 1296 px x 50 samples, 1 GHz NSB on every
 pixel, one signal pulse per pixel (1..3162 pe, top ~10 % of pixels saturate 12 bits).  A "step" is
 one pass of the hot path over one batch of `--events-per-step` events (default 16384 = 2.1 GB of
-ADC, far larger than the 126 MB L2) followed by the on-device validation statistics of that batch.
+ADC, far larger than the 126 MB L2) with the on-device validation statistics of that batch taken inside the generation kernel.
 At N>1 (torchrun, one rank per GPU) every rank generates its own contiguous range of the global
 event index (weak scaling, no data-path collective) and the statistics are all-reduced once at
 the end of the timed region (NCCL).
@@ -40,8 +40,10 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--events-per-step', type=int, default=16384)
-    ap.add_argument('--kernel', default='auto', choices=['auto', 'scatter', 'sweep'])
-    ap.add_argument('--workload', default='c4', choices=['c4', 'dark'])
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'scatter', 'sweep', 'tensor', 'grid'])
+    ap.add_argument('--workload', default='c4', choices=['c4', 'dark', 'acdc', 'grid'])
+    ap.add_argument('--separate-stats', action='store_true',
+                    help='statistics by the stand-alone kernel (a second pass over the cube) instead of fused into generation')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-events', type=int, default=3, help='timed oracle events per host worker')
@@ -52,6 +54,12 @@ def workload_kwargs(name):
     from digicamtoy_b200 import workloads
     if name == 'dark':
         return workloads.c1_dark(n_photon=0.), 'C1 dark.yml: 1296 px, 92 bins, NSB 3 MHz'
+    if name == 'acdc':
+        return workloads.c2_ac_dc(0.125, 10.), 'C2 ac_dc.yml level: 1296 px, 50 bins, NSB 0.125 GHz, n_photon 10'
+    if name == 'grid':
+        kw = workloads.c4_full_camera()
+        kw['sub_binning'] = 1
+        return kw, 'C4 geometry with on-grid NSB (sub_binning=1): 1296 px, 50 bins, NSB 1 GHz, n_photon 1..3162 pe'
     return workloads.c4_full_camera(), WORKLOAD
 
 
@@ -116,9 +124,11 @@ def run_reference_arm(a):
     # One oracle event per worker per "step".  A full-camera C4 event costs ~3.8 s on one core; if
     # steps + warm-up would run past ~150 s the sample is cut to a leading block of pixels
     # (cost per pixel is constant, so samples/s is unaffected).
-    sec_per_event = 3.8 if a.workload == 'c4' else 0.12
+    sec_per_event = {'c4': 3.8, 'grid': 3.8, 'acdc': 0.6}.get(a.workload, 0.12)
     est = sec_per_event * (a.steps + a.warmup)
     n_px = kwargs['n_pixels']
+    kwargs_full_pixels = n_px
+    n_bins_cfg = int((kwargs['time_end'] - kwargs['time_start']) // kwargs['time_sampling'])
     if est > 150.0:
         n_px = max(81, int(n_px * 150.0 / est))
         kwargs = subset_pixels(kwargs, n_px)
@@ -129,8 +139,9 @@ def run_reference_arm(a):
     line = dict(impl='reference', metric=METRIC, value=rate, unit=UNIT, n_gpus=a.gpus, steps=a.steps,
                 warmup=a.warmup, ms_per_step=per_step_ms, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f64', data='synthetic',
-                config=dict(workload=name, events_per_step=cores, pixels_per_event=n_px,
-                            timing='time.perf_counter around the oracle loop, per worker; value = sum over workers'),
+                config=dict(workload=name, n_pixels=kwargs_full_pixels, n_bins=n_bins_cfg),
+                run_details=dict(events_per_step=cores, pixels_per_event=n_px,
+                                 timing='time.perf_counter around the oracle loop, per worker; value = sum over workers'),
                 cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind='port', sample=sample),
                 e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -235,10 +246,14 @@ def run_b200_arm(a):
         out = ring[i & 1]
         if record is not None:
             record[0].record(stream)
-        gen.generate(E, first_event=first, out=out)
+        if a.separate_stats:
+            gen.generate(E, first_event=first, out=out)
+        else:
+            stats.generate(E, first_event=first, out=out)       # statistics fused into the generation kernel
         if record is not None:
             record[1].record(stream)
-        stats.accumulate(out)
+        if a.separate_stats:
+            stats.accumulate(out)
 
     def barrier():
         if world > 1:
@@ -336,12 +351,15 @@ def run_b200_arm(a):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=elapsed_ms / a.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic',
-                config=dict(workload=name, events_per_step_per_gpu=E, n_pixels=P, n_bins=B,
-                            kernel=gen.kernel, seed=workloads.C4_SEED,
-                            l2='each step writes %.2f GB per GPU into a 2-deep ring (>> 126 MB L2); no input re-read' % (algo_bytes / 1e9),
-                            sharding='contiguous global-event ranges per rank; one all-reduce of the statistics at the end'),
-                events_per_s=value / (P * B), roofline=roofline, e2e=e2e, gpu_launches=2 * a.steps,
-                gpu_launches_detail='per step: 1 x k_generate_%s + 1 x k_stats_tile' % gen.kernel,
+                config=dict(workload=name, n_pixels=P, n_bins=B),
+                run_details=dict(events_per_step_per_gpu=E, kernel=gen.kernel, seed=workloads.C4_SEED,
+                                 statistics='separate kernel' if a.separate_stats else 'fused into the generation kernel',
+                                 l2='each step writes %.2f GB per GPU into a 2-deep ring (>> 126 MB L2); no input re-read' % (algo_bytes / 1e9),
+                                 sharding='contiguous global-event ranges per rank; one all-reduce of the statistics at the end'),
+                events_per_s=value / (P * B), roofline=roofline, e2e=e2e,
+                gpu_launches=(2 if a.separate_stats else 1) * a.steps,
+                gpu_launches_detail=('per step: 1 x k_generate_%s + 1 x k_stats_tile' if a.separate_stats else
+                                     'per step: 1 x k_generate_%s (statistics fused)') % gen.kernel,
                 clocks=clocks.summary(w0, w1),
                 validation=dict(mean_adc=stats_result['moments'][0] / max(1, stats_result['n_events'] * P * B),
                                 n_events_reduced=stats_result['n_events'],

@@ -90,6 +90,7 @@ struct dct_handle {
     float* d_sig[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int16_t* h_stage[2] = {nullptr, nullptr};
     uint32_t chunk_events = 0;
+    bool pipeline_ready = false;
 };
 
 namespace {
@@ -164,19 +165,22 @@ void free_pipeline(dct_handle* h) {
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     h->s_gen = h->s_copy = nullptr;
     h->chunk_events = 0;
+    h->pipeline_ready = false;
 }
 
 template <bool POLY, int NT>
 int launch_scatter(dct_handle* h, const dct::GenArgs& a, cudaStream_t st) {
     auto kern = dct::k_generate_scatter<POLY, NT>;
+    const size_t smem = dct::smem_with_stats(h->gen_smem, a, NT);
+    if (smem > 227 * 1024) return fail(DCT_E_UNSUPPORTED, "trace too long for fused statistics");
     static thread_local size_t configured[16] = {0};
-    if (h->gen_smem > 48 * 1024 && configured[h->device & 15] < h->gen_smem) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gen_smem));
-        configured[h->device & 15] = h->gen_smem;
+    if (smem > 48 * 1024 && configured[h->device & 15] < smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[h->device & 15] = smem;
     }
     const uint64_t blocks = (a.n_traces + NT - 1) / NT;
     if (blocks > 0x7fffffffull) return fail(DCT_E_ARG, "too many traces for one launch");
-    kern<<<(unsigned)blocks, NT, h->gen_smem, st>>>(a);
+    kern<<<(unsigned)blocks, NT, smem, st>>>(a);
     CK(cudaGetLastError());
     return DCT_OK;
 }
@@ -452,8 +456,13 @@ void dct_destroy(dct_handle* h) {
 
 int dct_selected_kernel(const dct_handle* h) { return h ? h->kernel : DCT_E_ARG; }
 
+// histogram windows of the statistics kernels: centred on the expected pedestal (true_baseline,
+// host-computed); pulses only go up, so three quarters of a window lie above it
+static int stats_win_lo(const dct_handle* h, int win) { return (int)std::floor(h->mean_true_baseline) - win / 4; }
+
 static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
-                         float* sig_time, float* sig_charge, float* analog, void* stream) {
+                         float* sig_time, float* sig_charge, float* analog, void* stream,
+                         const dct::FusedStats* stats = nullptr) {
     if (!h || !adc) return fail(DCT_E_ARG, "handle or adc is NULL");
     if (n_events == 0) return DCT_OK;
     if ((first_event + n_events) >> 56) return fail(DCT_E_ARG, "event index exceeds 2^56");
@@ -467,6 +476,7 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
     a.adc = adc; a.sig_time = sig_time; a.sig_charge = sig_charge;
     a.table_in_smem = h->table_in_smem ? 1 : 0;
     a.analog = analog;
+    if (stats) a.st = *stats;
     if (h->kernel == DCT_KERNEL_TENSOR) {
         dct::TensorArgs ta;
         ta.g = a;
@@ -493,6 +503,26 @@ int dct_generate(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     return generate_impl(h, seed, first_event, n_events, adc, sig_time, sig_charge, nullptr, stream);
 }
 
+int dct_generate_stats(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
+                       float* sig_time, float* sig_charge, unsigned long long* adc_hist, double* bin_sum,
+                       double* bin_sumsq, double* pixel_sum, double* pixel_sumsq,
+                       unsigned long long* charge_hist, int32_t charge_lo, uint32_t n_charge_bins,
+                       double* moments, void* stream) {
+    if (!h) return fail(DCT_E_ARG, "handle is NULL");
+    if (!adc_hist || !bin_sum || !bin_sumsq || !pixel_sum || !pixel_sumsq)
+        return fail(DCT_E_ARG, "adc_hist, bin_sum, bin_sumsq, pixel_sum and pixel_sumsq are required");
+    if (charge_hist && n_charge_bins == 0) return fail(DCT_E_ARG, "n_charge_bins must be > 0");
+    const int n_hist = h->p.adc_max - h->p.adc_min + 1;
+    if (n_hist > 16384) return fail(DCT_E_UNSUPPORTED, "ADC histogram wider than 16384 bins");
+    dct::FusedStats st;
+    st.adc_hist = adc_hist; st.bin_sum = bin_sum; st.bin_sumsq = bin_sumsq;
+    st.pixel_sum = pixel_sum; st.pixel_sumsq = pixel_sumsq; st.charge_hist = charge_hist;
+    st.moments = moments; st.charge_lo = charge_lo; st.n_charge_bins = (int)n_charge_bins;
+    st.win_lo = stats_win_lo(h, dct::FS_WIN);
+    st.hist_lo = st.win_lo - dct::FS_HIST / 8;
+    return generate_impl(h, seed, first_event, n_events, adc, sig_time, sig_charge, nullptr, stream, &st);
+}
+
 int dct_generate_analog(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
                         float* analog, void* stream) {
     if (!analog) return fail(DCT_E_ARG, "analog is NULL");
@@ -506,19 +536,25 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
     CK(cudaSetDevice(h->device));
     const size_t trace_bytes = (size_t)h->p.P * h->p.B * sizeof(int16_t);
     const size_t sig_elems = (size_t)h->p.P * h->p.K;
-    if (!h->s_gen) {
+    if (!h->pipeline_ready) {
         // chunk ~64 MiB: large enough to amortise launches, small enough to pipeline
+        free_pipeline(h);                      // nothing half-built survives a failed earlier attempt
         uint32_t ce = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / trace_bytes);
         h->chunk_events = ce;
-        CK(cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
-            CK(cudaMalloc(&h->d_chunk[i], ce * trace_bytes));
-            CK(cudaMalloc(&h->d_sig[i][0], ce * sig_elems * sizeof(float)));
-            CK(cudaMalloc(&h->d_sig[i][1], ce * sig_elems * sizeof(float)));
+        cudaError_t e = cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_chunk[i], ce * trace_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_sig[i][0], ce * sig_elems * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_sig[i][1], ce * sig_elems * sizeof(float));
         }
+        if (e != cudaSuccess) {
+            free_pipeline(h);
+            return fail(DCT_E_CUDA, "host pipeline setup failed: %s", cudaGetErrorString(e));
+        }
+        h->pipeline_ready = true;
     }
     // Is the destination page-locked?  Then copy straight into it; otherwise go through pinned staging.
     cudaPointerAttributes attr;
@@ -526,46 +562,60 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
     if (cudaPointerGetAttributes(&attr, adc_host) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (!pinned && !h->h_stage[0])
-        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(&h->h_stage[i], h->chunk_events * trace_bytes));
+        for (int i = 0; i < 2; ++i) {
+            cudaError_t e = cudaMallocHost(&h->h_stage[i], h->chunk_events * trace_bytes);
+            if (e != cudaSuccess) {
+                free_pipeline(h);
+                return fail(DCT_E_CUDA, "pinned staging buffer: %s", cudaGetErrorString(e));
+            }
+        }
 
     const uint32_t ce = h->chunk_events;
     const uint32_t n_chunks = (n_events + ce - 1) / ce;
     struct Pending { int16_t* dst; size_t bytes; bool live; } pend[2] = {{nullptr, 0, false}, {nullptr, 0, false}};
-    for (uint32_t c = 0; c < n_chunks; ++c) {
+    // On any error: nothing may still be writing into the caller's buffer when we return.
+    int rc = DCT_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == DCT_OK) rc = fail(DCT_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    for (uint32_t c = 0; c < n_chunks && rc == DCT_OK; ++c) {
         const int slot = (int)(c & 1);
         const uint32_t e0 = c * ce, ne = std::min(ce, n_events - e0);
         // the slot's previous copy must have drained before we overwrite its device buffer
         if (c >= 2) {
-            CK(cudaEventSynchronize(h->ev_copy[slot]));
+            if (!cuda_ok(cudaEventSynchronize(h->ev_copy[slot]), "cudaEventSynchronize")) break;
             if (pend[slot].live) { memcpy(pend[slot].dst, h->h_stage[slot], pend[slot].bytes); pend[slot].live = false; }
         }
-        int rc = dct_generate(h, seed, first_event + e0, ne, h->d_chunk[slot],
-                              sig_time_host ? h->d_sig[slot][0] : nullptr,
-                              sig_charge_host ? h->d_sig[slot][1] : nullptr, h->s_gen);
-        if (rc) return rc;
-        CK(cudaEventRecord(h->ev_gen[slot], h->s_gen));
-        CK(cudaStreamWaitEvent(h->s_copy, h->ev_gen[slot], 0));
+        rc = dct_generate(h, seed, first_event + e0, ne, h->d_chunk[slot],
+                          sig_time_host ? h->d_sig[slot][0] : nullptr,
+                          sig_charge_host ? h->d_sig[slot][1] : nullptr, h->s_gen);
+        if (rc) break;
+        if (!cuda_ok(cudaEventRecord(h->ev_gen[slot], h->s_gen), "cudaEventRecord")) break;
+        if (!cuda_ok(cudaStreamWaitEvent(h->s_copy, h->ev_gen[slot], 0), "cudaStreamWaitEvent")) break;
         int16_t* dst = adc_host + (size_t)e0 * h->p.P * h->p.B;
         if (pinned) {
-            CK(cudaMemcpyAsync(dst, h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+            if (!cuda_ok(cudaMemcpyAsync(dst, h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
         } else {
-            CK(cudaMemcpyAsync(h->h_stage[slot], h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+            if (!cuda_ok(cudaMemcpyAsync(h->h_stage[slot], h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
             pend[slot].dst = dst; pend[slot].bytes = ne * trace_bytes; pend[slot].live = true;
         }
-        if (sig_time_host)
-            CK(cudaMemcpyAsync(sig_time_host + (size_t)e0 * sig_elems, h->d_sig[slot][0],
-                               ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy));
-        if (sig_charge_host)
-            CK(cudaMemcpyAsync(sig_charge_host + (size_t)e0 * sig_elems, h->d_sig[slot][1],
-                               ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy));
-        CK(cudaEventRecord(h->ev_copy[slot], h->s_copy));
+        if (sig_time_host &&
+            !cuda_ok(cudaMemcpyAsync(sig_time_host + (size_t)e0 * sig_elems, h->d_sig[slot][0],
+                                     ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
+        if (sig_charge_host &&
+            !cuda_ok(cudaMemcpyAsync(sig_charge_host + (size_t)e0 * sig_elems, h->d_sig[slot][1],
+                                     ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
+        if (!cuda_ok(cudaEventRecord(h->ev_copy[slot], h->s_copy), "cudaEventRecord")) break;
         // generation of the next chunk in this slot's sibling may start right away
     }
-    CK(cudaStreamSynchronize(h->s_copy));
-    for (int s = 0; s < 2; ++s)
-        if (pend[s].live) memcpy(pend[s].dst, h->h_stage[s], pend[s].bytes);
-    CK(cudaStreamSynchronize(h->s_gen));
-    return DCT_OK;
+    // drain both streams whatever happened, then hand over what was staged
+    const bool drained = cuda_ok(cudaStreamSynchronize(h->s_copy), "cudaStreamSynchronize") &
+                         cuda_ok(cudaStreamSynchronize(h->s_gen), "cudaStreamSynchronize");
+    if (drained)
+        for (int s2 = 0; s2 < 2; ++s2)
+            if (pend[s2].live) memcpy(pend[s2].dst, h->h_stage[s2], pend[s2].bytes);
+    return rc;
 }
 
 static int replay_common(bool f64, dct_handle* h, uint32_t n_events, const int64_t* nsb_offsets,
@@ -638,11 +688,14 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
     const bool fast = (a.B % 2 == 0) && a.B <= 128 && (reinterpret_cast<uintptr_t>(adc) & 15) == 0 &&
                       ((uint64_t)a.P * wpr) % 4 == 0 && ((uint64_t)dct::STATS_ROWS * wpr) % 4 == 0 &&
                       (adc_hist != nullptr || moments == nullptr) && n_hist <= 16384 &&
-                      std::max(std::abs(a.adc_min), std::abs(a.adc_max)) <= 11585;
+                      // 32-bit sums of squares: 32 rows per column sum, B samples per trace
+                      std::max(std::abs(a.adc_min), std::abs(a.adc_max)) <= 11585 &&
+                      (uint64_t)a.B * (uint64_t)std::max(std::abs(a.adc_min), std::abs(a.adc_max)) *
+                              (uint64_t)std::max(std::abs(a.adc_min), std::abs(a.adc_max)) < (1ull << 32);
     if (fast) {
         // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
         // the charge of a trace that holds nothing but that pedestal shift
-        const int win_lo = (int)std::floor(h->mean_true_baseline) - dct::STATS_WIN / 4;   // pulses only go up
+        const int win_lo = stats_win_lo(h, dct::STATS_WIN);
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
         int charge_win_lo = (int)std::floor(q0) - dct::STATS_CHARGE_WIN / 2;
         charge_win_lo = std::max(0, std::min(charge_win_lo, std::max(0, (int)n_charge_bins - dct::STATS_CHARGE_WIN)));

@@ -18,6 +18,7 @@
 // the int16 result into the front of the same row, so no second staging buffer is needed.
 #pragma once
 #include "device_params.cuh"
+#include "fused_stats.cuh"
 #include "sampling.cuh"
 
 namespace dct {
@@ -68,7 +69,15 @@ struct GenArgs {
     float* sig_charge;
     int table_in_smem;          // generic coef32 table staged in shared memory
     float* analog = nullptr;    // test hook: [n_traces, B] analog sums (p.e.-weighted template) before digitisation
+    FusedStats st;              // on-device statistics taken before the store (st.adc_hist == nullptr: off)
 };
+
+// dynamic shared memory of a generation kernel: its own `base` bytes, then (statistics on) the
+// fused-statistics scratch on a 16-byte boundary
+__host__ __device__ inline size_t stats_offset(size_t base) { return (base + 15) & ~(size_t)15; }
+inline size_t smem_with_stats(size_t base, const GenArgs& a, int nt) {
+    return a.st.adc_hist ? stats_offset(base) + fused_stats_smem(nt, a.p.B) : base;
+}
 
 // test hook of every generation kernel: the analog sums a trace is digitised from
 __device__ __forceinline__ void dump_analog(const GenArgs& a, uint64_t g, const float* row) {
@@ -408,6 +417,9 @@ k_generate_scatter(const GenArgs a) {
         digitise_trace(p, t, row);
     }
     __syncthreads();
+    if (a.st.adc_hist)
+        cta_fused_stats<NT, 1>(a.st, p, trace0, a.n_traces, rows,
+                               smem_raw + stats_offset(gen_smem_bytes(B, n_tab, NT)));
     store_run<NT>(a, trace0, rows);
 }
 

@@ -80,12 +80,14 @@ k_generate_grid(const GridArgs ga) {
         digitise_trace(p, t, row);
     }
     __syncthreads();
+    if (a.st.adc_hist)
+        cta_fused_stats<NT, 1>(a.st, p, trace0, a.n_traces, rows, smem_raw + stats_offset(grid_smem_bytes(B)));
     store_run<NT>(a, trace0, rows);
 }
 
 inline int launch_grid(int device, const GenArgs& a, const float* taps, cudaStream_t st, char* err, size_t err_len) {
     auto kern = k_generate_grid<GRID_THREADS>;
-    const size_t smem = grid_smem_bytes(a.p.B);
+    const size_t smem = smem_with_stats(grid_smem_bytes(a.p.B), a, GRID_THREADS);
     static thread_local size_t configured[16] = {0};
     if (smem > 48 * 1024 && configured[device & 15] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

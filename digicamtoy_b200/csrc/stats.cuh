@@ -294,11 +294,13 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
                 pix_s += ts;
                 pix_q += tq;
                 if (a.charge_hist) {
+                    // clamp first (as k_stats does), then the CTA window: with fewer than
+                    // STATS_CHARGE_WIN bins the window would otherwise swallow charges past the end
                     const long long bin = (long long)ts - charge_ref - a.charge_lo;
                     const long long cw = bin - charge_win_lo;
-                    if (cw >= 0 && cw < STATS_CHARGE_WIN) atomicAdd(&charge_s[cw], 1u);
-                    else if (bin >= a.n_charge_bins - 1) ++n_charge_over;
+                    if (bin >= a.n_charge_bins - 1) ++n_charge_over;
                     else if (bin <= 0) ++n_charge_under;
+                    else if (cw >= 0 && cw < STATS_CHARGE_WIN) atomicAdd(&charge_s[cw], 1u);
                     else atomicAdd(a.charge_hist + bin, 1ull);
                 }
             }

@@ -256,12 +256,15 @@ k_generate_sweep(const GenArgs a) {
         digitise_trace(p, t, row);
     }
     __syncthreads();
+    if (a.st.adc_hist)
+        cta_fused_stats<NT, 1>(a.st, p, trace0, a.n_traces, rows,
+                               smem_raw + stats_offset(gen_smem_bytes(B, TAPS * PHASES, NT)));
     store_run<NT>(a, trace0, rows);
 }
 
 inline int launch_sweep(int device, int /*sm_count*/, const GenArgs& a, cudaStream_t st, char* err, size_t err_len) {
     auto kern = k_generate_sweep<SWEEP_TAPS, SWEEP_PHASES, SWEEP_THREADS>;
-    const size_t smem = gen_smem_bytes(a.p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS);
+    const size_t smem = smem_with_stats(gen_smem_bytes(a.p.B, SWEEP_TAPS * SWEEP_PHASES, SWEEP_THREADS), a, SWEEP_THREADS);
     static thread_local size_t configured[16] = {0};
     if (smem > 48 * 1024 && configured[device & 15] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -54,10 +54,10 @@ constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #define DCT_TC_MIN_BLOCKS 4
 #endif
 #ifndef DCT_TC_POLL_NS
-#define DCT_TC_POLL_NS 200                     // sleep of the MMA warp between two looks at the producers' positions
+#define DCT_TC_POLL_NS 1000                    // longest the MMA warp sleeps before it looks at the producers' positions by itself
 #endif
 #ifndef DCT_TC_UNROLL
-#define DCT_TC_UNROLL 2                        // photo-electrons per lane between two looks at the ring state
+#define DCT_TC_UNROLL 4                        // photo-electrons per lane between two looks at the ring state
 #endif
 // mean pe per trace from which AUTO prefers this kernel over the sweep kernel.  1e30 = never:
 // measured on C4 (245 pe / trace) the first version needs 84 ms per 16384 events against the
@@ -148,6 +148,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
+}
+// one look at a phase with a hardware-suspended wait of up to `ns` nanoseconds; true = the phase is over
+__device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return done != 0;
+}
+
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -232,11 +245,13 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
     unsigned char* g_tiles = smem_raw + (ring_bytes > rows_bytes ? ring_bytes : rows_bytes);   // hi, lo, hi', lo'
     uint32_t* ctl = reinterpret_cast<uint32_t*>(g_tiles + 4 * TC_G_BYTES);
     // ctl[0..3]: cell every lane of producer warp w has reached; ctl[4]: cells released by the MMA
-    // warp; ctl[5]: TMEM base; ctl[8..9]: mbarrier the MMAs commit to
+    // warp; ctl[5]: TMEM base; ctl[8..9]: mbarrier the MMAs commit to; ctl[10..11]: mbarrier a
+    // producer warp flips whenever it publishes a new position (wakes the MMA warp)
     uint32_t* warp_pos = ctl;
     uint32_t* released = ctl + 4;
     uint32_t* tmem_slot = ctl + 5;
     const uint32_t bar = tc::smem_u32(ctl + 8);
+    const uint32_t notify = tc::smem_u32(ctl + 10);
 
     // ---- one-time setup
     {
@@ -247,6 +262,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         if (tid < 5) ctl[tid] = 0;          // not ctl[5]: tcgen05.alloc (warp 4) writes it concurrently
         if (tid == 0) {
             tc::mbar_init(bar, 1);
+            tc::mbar_init(notify, 1);          // every arrival completes a phase
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -281,16 +297,19 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         const uint32_t ring_addr = tc::smem_u32(ring);
         const uint32_t g_addr = tc::smem_u32(g_tiles);
         int slot_i = 0;
+        uint32_t notify_parity = 0;
         for (int c = 0; c < n_cells; ++c) {
             const uint32_t slot = ring_addr + (uint32_t)slot_i * TC_SLOT_BYTES;
             if (warp == 4) {
-                // wait until every producer warp is past cell c
+                // wait until every producer warp is past cell c: sleep on the notify barrier (a
+                // producer flips it with every new position).  A stale parity only costs one more
+                // look, a missed flip at most DCT_TC_POLL_NS.
                 uint32_t spins = 0;
                 while (true) {
                     const uint32_t m = min(min(tc::ld_volatile(warp_pos), tc::ld_volatile(warp_pos + 1)),
                                            min(tc::ld_volatile(warp_pos + 2), tc::ld_volatile(warp_pos + 3)));
                     if (m > (uint32_t)c) break;
-                    __nanosleep(DCT_TC_POLL_NS);
+                    if (tc::mbar_try_wait_ns(notify, notify_parity, DCT_TC_POLL_NS)) notify_parity ^= 1u;
                     if (++spins > (1u << 24)) __trap();
                 }
                 __threadfence_block();
@@ -383,8 +402,11 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     acc3 = __fmaf_rn(acc3, keep, m3);
                     const __half2 h01 = __floats2half2_rn(acc0, acc1);
                     const __half2 h23 = __floats2half2_rn(acc2, acc3);
-                    const uint32_t addr = row_off + ((gi >> 3) % (uint32_t)RING) * TC_SLOT_BYTES +
-                                          (((gi & 6u) << 6) | ((gi & 1u) << 3));
+                    // slot of the cell + place of interval j in the row: (j >> 1) 128 + (j & 1) 8 bytes,
+                    // from a byte table (PRMT) -- {0, 1, 16, 17, 32, 33, 48, 49} x 8
+                    const uint32_t cellq = gi >> 3;
+                    const uint32_t joff8 = __byte_perm(0x11100100u, 0x31302120u, gi & 7u);
+                    const uint32_t addr = row_off + (cellq % (uint32_t)RING) * TC_SLOT_BYTES + (joff8 << 3);
                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
                                  :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
                                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
@@ -396,7 +418,10 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             if (wmin > warp_done) {
                 tc::fence_async_proxy();
                 __syncwarp();
-                if (lane == 0) tc::st_volatile(warp_pos + warp, min(wmin, (uint32_t)n_cells));
+                if (lane == 0) {
+                    tc::st_volatile(warp_pos + warp, min(wmin, (uint32_t)n_cells));
+                    tc::mbar_arrive(notify);
+                }
                 warp_done = wmin;
             }
             if (wmin >= (uint32_t)n_cells) break;
@@ -445,6 +470,9 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             digitise_trace(p, t, row);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (a.st.adc_hist)
+            cta_fused_stats<TC_TRACES, 1>(a.st, p, trace0, a.n_traces, rows,
+                                          smem_raw + stats_offset(tensor_smem_bytes(B, RING)));
         store_run<TC_TRACES>(a, trace0, rows);
     }
     tc::fence_before();
@@ -457,7 +485,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
 
 inline int launch_tensor(int device, const TensorArgs& ta, cudaStream_t st, char* err, size_t err_len) {
     auto kern = ta.check_span ? k_generate_tensor<DCT_TC_RING, true> : k_generate_tensor<DCT_TC_RING, false>;
-    const size_t smem = tensor_smem_bytes(ta.g.p.B, DCT_TC_RING);
+    const size_t smem = smem_with_stats(tensor_smem_bytes(ta.g.p.B, DCT_TC_RING), ta.g, TC_TRACES);
     static thread_local size_t configured[16][2] = {{0}};
     if (configured[device & 15][ta.check_span] < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -17,14 +17,14 @@ LIB_NAME = 'libdigicamtoy_sm100.so'
 LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
 CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
 
-DCT_ABI_VERSION = 1
+DCT_ABI_VERSION = 2
 KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP, KERNEL_GRID, KERNEL_TENSOR = 0, 1, 2, 3, 4
 KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep', KERNEL_GRID: 'grid',
                 KERNEL_TENSOR: 'tensor'}
 
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',
-    'dct_generate', 'dct_generate_analog', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
+    'dct_generate', 'dct_generate_stats', 'dct_generate_analog', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
     'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe',
 )
 
@@ -83,6 +83,7 @@ def load_library():
     lib.dct_generate_analog.argtypes = [vp, u64, u64, u32, vp, vp, vp]
     for f in (lib.dct_replay_f64, lib.dct_replay_f32):
         f.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dct_generate_stats.argtypes = [vp, u64, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
     lib.dct_stats_accumulate.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
     lib.dct_write_calibrate.argtypes = [vp, ctypes.c_size_t, vp]
     lib.dct_trace_pe.argtypes = [vp, u64, u64, u32, u32, vp, vp, vp, vp, vp]
@@ -151,6 +152,13 @@ class Handle:
                  stream=None):
         check(self.lib.dct_generate(self.ptr, seed, first_event, n_events, adc_ptr, sig_time_ptr,
                                     sig_charge_ptr, stream))
+
+    def generate_stats(self, seed, first_event, n_events, adc_ptr, sig_time_ptr=None, sig_charge_ptr=None,
+                       adc_hist=None, bin_sum=None, bin_sumsq=None, pixel_sum=None, pixel_sumsq=None,
+                       charge_hist=None, charge_lo=0, n_charge_bins=0, moments=None, stream=None):
+        check(self.lib.dct_generate_stats(self.ptr, seed, first_event, n_events, adc_ptr, sig_time_ptr,
+                                          sig_charge_ptr, adc_hist, bin_sum, bin_sumsq, pixel_sum, pixel_sumsq,
+                                          charge_hist, charge_lo, n_charge_bins, moments, stream))
 
     def generate_analog(self, seed, first_event, n_events, adc_ptr, analog_ptr, stream=None):
         check(self.lib.dct_generate_analog(self.ptr, seed, first_event, n_events, adc_ptr, analog_ptr, stream))

@@ -56,6 +56,33 @@ class CubeStats:
             moments=self._ptr(f, self._slices_f['moments']), stream=stream)
         i[self._slices_i['n_events']] += n_events
 
+    def generate(self, n_events, first_event=0, out=None, stream=None):
+        """Generate ``n_events`` events with the statistics taken inside the generation kernel
+        (``dct_generate_stats``): the cube lands in ``out`` as usual but is never read back."""
+        torch = self._torch
+        g, p = self.gen, self.gen.params
+        dev = torch.device('cuda', g.device)
+        n_events = int(n_events)
+        if out is None:
+            out = torch.empty((n_events, p.n_pixels, p.n_bins), dtype=torch.int16, device=dev)
+        elif (out.dtype != torch.int16 or not out.is_contiguous() or out.device != dev
+              or out.numel() != n_events * p.n_pixels * p.n_bins):
+            raise ValueError('out must be a contiguous int16 CUDA tensor of n*P*B elements')
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        f, i = self._f, self._i
+        if n_events:
+            g._handle.generate_stats(
+                g.seed, int(first_event), n_events, out.data_ptr(), None, None,
+                adc_hist=self._ptr(i, self._slices_i['adc_hist']),
+                bin_sum=self._ptr(f, self._slices_f['bin_sum']), bin_sumsq=self._ptr(f, self._slices_f['bin_sumsq']),
+                pixel_sum=self._ptr(f, self._slices_f['pixel_sum']), pixel_sumsq=self._ptr(f, self._slices_f['pixel_sumsq']),
+                charge_hist=self._ptr(i, self._slices_i['charge_hist']) if self.with_charge else None,
+                charge_lo=self.charge_lo, n_charge_bins=self.n_charge_bins,
+                moments=self._ptr(f, self._slices_f['moments']), stream=stream)
+            i[self._slices_i['n_events']] += n_events
+        return out
+
     def all_reduce(self, group=None):
         """Sum over ranks (the only collective of a sharded run; a few tens of KB)."""
         import torch.distributed as dist

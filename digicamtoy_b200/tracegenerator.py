@@ -248,6 +248,9 @@ class NTraceGenerator:
             adc = torch.empty((n_events, p.n_pixels, p.n_bins), dtype=torch.int16).pin_memory()
         else:
             adc = out
+            if (not isinstance(adc, torch.Tensor) or adc.dtype != torch.int16 or adc.is_cuda
+                    or not adc.is_contiguous() or adc.numel() != n_events * p.n_pixels * p.n_bins):
+                raise ValueError('out must be a contiguous int16 CPU tensor of n*P*B elements')
         t = q = None
         if truth:
             t = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DCT_ABI_VERSION 1
+#define DCT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DCT_API __attribute__((visibility("default")))
@@ -160,6 +160,18 @@ DCT_API int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_e
                          unsigned long long* adc_hist, double* bin_sum, double* bin_sumsq,
                          double* pixel_sum, double* pixel_sumsq, unsigned long long* charge_hist,
                          int32_t charge_lo, uint32_t n_charge_bins, double* moments, void* stream);
+
+/* dct_generate with the statistics of dct_stats_accumulate taken inside the generation kernel, from the
+ * digitised samples in shared memory just before they are stored: same results bit for bit (power
+ * sums: to float64 rounding), no second pass over the cube.  adc_hist, bin_sum, bin_sumsq, pixel_sum
+ * and pixel_sumsq are required; charge_hist and moments may be NULL.  All buffers accumulate.
+ * Replaces the host-side analysis of reference nsb_baseline.py:21-32 for cubes that are generated
+ * and analysed in one go. */
+DCT_API int dct_generate_stats(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
+                       int16_t* adc, float* sig_time, float* sig_charge,
+                       unsigned long long* adc_hist, double* bin_sum, double* bin_sumsq,
+                       double* pixel_sum, double* pixel_sumsq, unsigned long long* charge_hist,
+                       int32_t charge_lo, uint32_t n_charge_bins, double* moments, void* stream);
 
 /* Write-only calibration kernel: streams n int16 values to buf with the same 16-byte stores the
  * generator uses.  Its GB/s is the practical ceiling of the HBM-write roofline. */

@@ -1,9 +1,7 @@
-# tensor kernel under build variants ($@ = one EXTRA string per variant), 64 and 1024 events
+# tensor kernel under build variants ($@ = one EXTRA string per variant): parity on 64 events + timing on 16384
 mkdir -p gpurun_out
 for V in "$@"; do
   (cd digicamtoy_b200/csrc && rm -f ../libdigicamtoy_sm100.so && make EXTRA="$V" > /dev/null 2>&1)
   echo "=== variant: $V"
-  for ev in 64 1024; do
-    TC_EVENTS=$ev TC_TIME=0 CUDA_LAUNCH_BLOCKING=1 timeout 120 python scripts/tensor_check.py 2>&1 | grep -E "analog diff|adc:|rror:" | head -3
-  done
+  TC_EVENTS=64 TC_TIME_EVENTS=16384 timeout 300 python scripts/tensor_check.py 2>&1 | grep -E "analog diff|adc:|tensor:|rror:" | head -4
 done

@@ -33,7 +33,8 @@ def test_b200_arm_json_line():
     assert r['achieved'] > 5 and r['traffic'] is not None
     e = j['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 2048 * 1296 * 50 * 2
-    assert j['gpu_launches'] == 6 and j['value'] > 1e9
+    assert j['gpu_launches'] == 3 and j['value'] > 1e9            # one fused generation + statistics kernel per step
+    assert set(j['config']) == {'workload', 'n_pixels', 'n_bins'}
     assert j['validation']['n_events_reduced'] == 3 * 2048
     assert 300 < j['validation']['mean_adc'] < 500
 
@@ -43,3 +44,4 @@ def test_reference_arm_json_line():
     assert j['impl'] == 'reference' and j['unit'] == 'samples/s' and j['value'] > 0
     assert j['cpu_baseline']['kind'] == 'port' and j['cpu_baseline']['cores'] >= 1
     assert j['e2e']['value'] == j['value'] and j['e2e']['h2d_bytes_per_step'] == 0
+    assert set(j['config']) == {'workload', 'n_pixels', 'n_bins'} and j['config']['n_bins'] == 92     # same keys as the b200 arm

@@ -107,7 +107,7 @@ def test_baseline_std_versus_nsb_rate_and_gain_example():
     against the oracle."""
     nsb_rates = np.logspace(-0.5, 1.2, 10)
     gains = np.linspace(3, 5, 5)
-    worst = 0.0
+    worst, spread_ratio = 0.0, []
     for gain in gains:
         for rate in nsb_rates:
             kw = dict(n_pixels=1, time_end=200, nsb_rate=float(rate), gain=float(gain), baseline=10)
@@ -119,9 +119,13 @@ def test_baseline_std_versus_nsb_rate_and_gain_example():
             z = (mine.mean() - ref.mean()) / se
             worst = max(worst, abs(z))
             assert abs(z) < 4.5, (gain, rate, mine.mean(), ref.mean(), z)
-            # the spread the example reports as 'sde_of_mean' (std / sqrt(N)) agrees as well
-            assert abs(mine.std() / ref.std() - 1) < 0.35, (gain, rate, mine.std(), ref.std())
+            # the spread the example reports as 'sde_of_mean' (std / sqrt(N)): per-trace std values have
+            # a long upper tail, so a spread estimated from 100 oracle events scatters by tens of percent
+            # (1.02 .. 1.78 between blocks of 100 at gain 3, 2.8 GHz) -- each point loosely, the grid sharply
+            spread_ratio.append(mine.std() / ref.std())
+            assert 0.5 < spread_ratio[-1] < 2.0, (gain, rate, mine.std(), ref.std())
     assert worst > 0.0
+    assert abs(np.mean(np.log(spread_ratio))) < 0.08, np.mean(np.log(spread_ratio))
 
 
 KAT_MAPPING = dict(gain_nsb=1 / 0.85, gain=5.8, baseline=500, sigma_e=0.8, sigma_1=0.8, crosstalk=0.08,
@@ -165,6 +169,7 @@ def test_reference_npz_measured_rows_versus_number_of_waveforms():
     assert z['mean'].shape == (4, 30) and int(z['trials']) == 100
     trials = 400
     for row, n_w in enumerate(z['n_waveforms'].astype(int)):
+        ratios = []
         for i in range(0, 30):
             rate = float(z['nsb_rate'][i])
             g = _gen(seed=100 + row, n_pixels=trials, nsb_rate=rate, **KAT_MAPPING)
@@ -182,6 +187,10 @@ def test_reference_npz_measured_rows_versus_number_of_waveforms():
             assert abs(t_mean.mean() - ref_mean) < 0.03 * shift + 0.06 + stat, (n_w, rate, t_mean.mean(), ref_mean)
             stat = 4 * np.hypot(ref_std_err / 10., t_std.std() / np.sqrt(trials))
             assert abs(t_std.mean() - ref_std) < 0.05 * ref_std + stat, (n_w, rate, t_std.mean(), ref_std)
-            # spreads over trials: a standard deviation estimated from 100 trials is good to ~7 %
-            assert abs(t_mean.std() / ref_mean_err - 1) < 0.35, (n_w, rate, t_mean.std(), ref_mean_err)
-            assert abs(t_std.std() / ref_std_err - 1) < 0.35, (n_w, rate, t_std.std(), ref_std_err)
+            # spreads over trials: at low rates a trial's std is dominated by whether it caught a pe
+            # pulse or not, so a spread estimated from 100 trials scatters by tens of percent -- each
+            # point loosely, the 30 points of a row together sharply
+            ratios.append((t_mean.std() / ref_mean_err, t_std.std() / ref_std_err))
+            assert 0.4 < ratios[-1][0] < 2.5 and 0.4 < ratios[-1][1] < 2.5, (n_w, rate, ratios[-1])
+        log_ratio = np.log(np.array(ratios)).mean(axis=0)
+        assert np.abs(log_ratio).max() < 0.1, (n_w, log_ratio)

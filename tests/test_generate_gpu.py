@@ -524,6 +524,56 @@ def test_stats_kernel_synthetic_extremes():
     _check_stats_against_numpy(g, out, charge_lo=-1000, n_charge_bins=5000)
 
 
+FUSED_CASES = [
+    ('sweep-acdc', dict(n_pixels=200, nsb_rate=0.3, n_photon=5., **ACDC), 150, 'sweep'),
+    ('sweep-dark-92', dict(n_pixels=130, n_photon=2., **DARK), 200, 'sweep'),
+    ('sweep-bright', dict(n_pixels=130, n_photon=[[3000.]] * 65 + [[40.]] * 65, **{**DARK, 'time_signal': 100.}), 100, 'sweep'),
+    ('scatter-odd-bins', dict(n_pixels=20, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 204}), 60, 'scatter'),
+    ('scatter-lowgain', dict(n_pixels=77, nsb_rate=0.5, gain_nsb=1 / 0.85, baseline=500,
+                             pulse_shape_file='utils/pulse_SST-1M_AfterPreampLowGain.dat'), 80, 'scatter'),
+    ('grid', dict(n_pixels=100, nsb_rate=0.5, n_photon=5., sub_binning=1, **ACDC), 100, 'grid'),
+    ('tensor', dict(n_pixels=150, nsb_rate=1.0, n_photon=50., **ACDC), 90, 'tensor'),
+    ('negative-rail', dict(n_pixels=40, baseline=1, nsb_rate=0.01, sigma_e=2.0, n_photon=0), 120, 'sweep'),
+]
+
+
+@pytest.mark.parametrize('name,kw,n_events,kernel', FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_statistics_equal_the_separate_kernel_and_numpy(name, kw, n_events, kernel):
+    """dct_generate_stats (statistics taken inside the generation kernel) against
+    dct_generate + dct_stats_accumulate on the same events, and both against NumPy: same cube, same
+    histogram / sums bit for bit (integers < 2^53 in float64), power sums to rounding."""
+    import torch
+    from digicamtoy_b200.stats import CubeStats
+    g = gen(seed=21, kernel=kernel, **kw)
+    assert g.kernel == kernel
+    fused = CubeStats(g, charge_lo=-300, n_charge_bins=2500)
+    first = 0
+    cubes = []
+    for n in (n_events // 3, n_events - n_events // 3):        # buffers accumulate over calls
+        cubes.append(fused.generate(n, first_event=first))
+        first += n
+    cube_f = torch.cat(cubes)
+    plain = g.generate(n_events, first_event=0)
+    torch.cuda.synchronize()
+    assert torch.equal(cube_f, plain)                           # statistics do not touch the cube
+    sep = CubeStats(g, charge_lo=-300, n_charge_bins=2500)
+    sep.accumulate(plain)
+    a, b = fused.result(), sep.result()
+    assert a['n_events'] == b['n_events'] == n_events
+    for key in ('adc_hist', 'charge_hist', 'bin_sum', 'bin_sumsq', 'pixel_sum', 'pixel_sumsq'):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.allclose(a['moments'], b['moments'], rtol=1e-12)
+    _check_stats_against_numpy(g, plain, charge_lo=-300, n_charge_bins=2500)
+
+
+def test_fused_statistics_need_their_buffers():
+    import torch
+    g = gen(n_pixels=8, nsb_rate=0.1, seed=1)
+    out = torch.empty((2, 8, 50), dtype=torch.int16, device='cuda')
+    with pytest.raises(ValueError):
+        g._handle.generate_stats(g.seed, 0, 2, out.data_ptr())
+
+
 def test_write_calibrate_kernel():
     import torch
     from digicamtoy_b200 import native

@@ -147,6 +147,7 @@ def test_hdf5_branch_of_the_writer_with_a_stub_h5py(tmp_path, monkeypatch):
 
         def close(self):
             self.closed = True
+            open(self.filename, 'wb').close()               # the real h5py leaves a file behind
 
     stub = types.ModuleType('h5py')
     stub.File = File
@@ -157,7 +158,9 @@ def test_hdf5_branch_of_the_writer_with_a_stub_h5py(tmp_path, monkeypatch):
     w.put('config/pulse_shape_file', 'utils/x.dat')
     w.put('data/adc_count', np.zeros((2, 3, 4), dtype=np.int16), compress=True, dtype=np.uint16)
     w.put('data/true_baseline', np.zeros(3), compress=True)
+    assert w.h5.filename.endswith('f.hdf5.part')            # written under a temporary name ...
     assert w.close().endswith('f.hdf5') and w.h5.closed
+    assert (tmp_path / 'f.hdf5').exists() and not (tmp_path / 'f.hdf5.part').exists()      # ... renamed when complete
     assert calls[0] == ('config', 'n_pixels', (), {})
     assert calls[1] == ('config', 'pulse_shape_file', 'str', {})
     assert calls[2] == ('data', 'adc_count', (2, 3, 4), dict(chunks=True, compression='gzip', dtype=np.uint16))
