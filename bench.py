@@ -6,7 +6,7 @@
 Workload (N=1): BASELINE.json config C4 -- full camera, 1296 px x 50 samples, 1 GHz NSB on every
 pixel, one signal pulse per pixel (1..3162 pe, top ~10 % of pixels saturate 12 bits).  A "step" is
 one pass of the hot path over one batch of `--events-per-step` events (default 16384 = 2.1 GB of
-ADC, far larger than the 126 MB L2) with the on-device validation statistics of that batch taken inside the generation kernel.
+ADC, far larger than the 126 MB L2) followed by the on-device validation statistics of that batch.
 At N>1 (torchrun, one rank per GPU) every rank generates its own contiguous range of the global
 event index (weak scaling, no data-path collective) and the statistics are all-reduced once at
 the end of the timed region (NCCL).
@@ -42,8 +42,10 @@ def parse():
     ap.add_argument('--events-per-step', type=int, default=16384)
     ap.add_argument('--kernel', default='auto', choices=['auto', 'scatter', 'sweep', 'tensor', 'grid'])
     ap.add_argument('--workload', default='c4', choices=['c4', 'dark', 'acdc', 'grid'])
-    ap.add_argument('--separate-stats', action='store_true',
-                    help='statistics by the stand-alone kernel (a second pass over the cube) instead of fused into generation')
+    ap.add_argument('--fused-stats', action='store_true',
+                    help='statistics taken inside the generation kernel (dct_generate_stats) instead of by the stand-alone '
+                         'kernel.  Measured slower (dark.yml 8.7 against 7.2 ms per step, C4 62.3 against 61.9): the '
+                         'statistics are instruction-bound, not HBM-bound, so the saved read of the cube buys nothing')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-events', type=int, default=3, help='timed oracle events per host worker')
@@ -246,13 +248,13 @@ def run_b200_arm(a):
         out = ring[i & 1]
         if record is not None:
             record[0].record(stream)
-        if a.separate_stats:
+        if (not a.fused_stats):
             gen.generate(E, first_event=first, out=out)
         else:
             stats.generate(E, first_event=first, out=out)       # statistics fused into the generation kernel
         if record is not None:
             record[1].record(stream)
-        if a.separate_stats:
+        if (not a.fused_stats):
             stats.accumulate(out)
 
     def barrier():
@@ -311,6 +313,23 @@ def run_b200_arm(a):
                    api='NTraceGenerator.generate_host -> dct_generate_host (pinned host buffer, chunked D2H overlapped with generation)',
                    host_cpus_rank0=(cpus if isinstance(cpus, str) else '%d cpus: %s..%s' % (len(cpus), cpus[0], cpus[-1])))
         del host
+    # ---- the reference's own way of consuming the generator: `for event in generator`
+    # (reference produce_data.py:119-126), one event at a time out of prefetched pinned batches
+    iterator = None
+    if rank == 0 and not a.no_e2e:
+        n_it = 8192 if B <= 64 else 4096
+        it_gen = NTraceGenerator(seed=workloads.C4_SEED + 1, device=local, kernel=a.kernel, **kwargs)
+        n_warm = 2 * it_gen.batch_events + 1           # both pinned batch slots and the host pipeline exist after this
+        sink = 0
+        for _ in range(n_warm):
+            sink += int(next(it_gen).adc_count[0, 0])
+        i0 = time.perf_counter()
+        for _ in range(n_it):
+            sink += int(next(it_gen).adc_count[0, 0])  # touch the event like a consumer would
+        i_s = time.perf_counter() - i0
+        iterator = dict(events_per_s=n_it / i_s, events=n_it, warmup_events=n_warm, batch_events=it_gen.batch_events,
+                        api='for event in NTraceGenerator(...): event.adc_count (two pinned batch slots, next batch prefetched)')
+        it_gen.close()
     if rank == 0:
         clocks.stop()
 
@@ -353,12 +372,13 @@ def run_b200_arm(a):
                 dtype='f32', data='synthetic',
                 config=dict(workload=name, n_pixels=P, n_bins=B),
                 run_details=dict(events_per_step_per_gpu=E, kernel=gen.kernel, seed=workloads.C4_SEED,
-                                 statistics='separate kernel' if a.separate_stats else 'fused into the generation kernel',
+                                 statistics='separate kernel' if (not a.fused_stats) else 'fused into the generation kernel',
                                  l2='each step writes %.2f GB per GPU into a 2-deep ring (>> 126 MB L2); no input re-read' % (algo_bytes / 1e9),
                                  sharding='contiguous global-event ranges per rank; one all-reduce of the statistics at the end'),
-                events_per_s=value / (P * B), roofline=roofline, e2e=e2e,
-                gpu_launches=(2 if a.separate_stats else 1) * a.steps,
-                gpu_launches_detail=('per step: 1 x k_generate_%s + 1 x k_stats_tile' if a.separate_stats else
+                events_per_s=value / (P * B), roofline=roofline, e2e=e2e, iterator=iterator,
+                iterator_events_per_s=iterator['events_per_s'] if iterator else None,
+                gpu_launches=(2 if (not a.fused_stats) else 1) * a.steps,
+                gpu_launches_detail=('per step: 1 x k_generate_%s + 1 x k_stats_tile' if (not a.fused_stats) else
                                      'per step: 1 x k_generate_%s (statistics fused)') % gen.kernel,
                 clocks=clocks.summary(w0, w1),
                 validation=dict(mean_adc=stats_result['moments'][0] / max(1, stats_result['n_events'] * P * B),

@@ -471,6 +471,7 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
     dct::GenArgs a;
     a.p = h->p;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.rk = dct::make_round_keys(a.k0, a.k1);
     a.first_event = first_event;
     a.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
     a.adc = adc; a.sig_time = sig_time; a.sig_charge = sig_charge;
@@ -484,10 +485,6 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
         ta.n_cells = h->tc_n_cells; ta.col_shift = h->tc_col_shift; ta.v_scale = h->tc_v_scale;
         ta.check_span = h->tc_check_span;
         ta.y0 = h->tc_y0; ta.y_end = h->tc_y_end;
-        for (int r = 0; r < DCT_PHILOX_ROUNDS; ++r) {
-            ta.rk[2 * r] = a.k0 + (uint32_t)r * 0x9E3779B9u;
-            ta.rk[2 * r + 1] = a.k1 + (uint32_t)r * 0xBB67AE85u;
-        }
         return dct::launch_tensor(h->device, ta, st, g_err, sizeof(g_err));
     }
     if (h->kernel == DCT_KERNEL_GRID) return dct::launch_grid(h->device, a, h->grid_tap, st, g_err, sizeof(g_err));
@@ -760,6 +757,7 @@ int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     dct::DumpArgs d;
     d.g.p = h->p;
     d.g.k0 = (uint32_t)seed; d.g.k1 = (uint32_t)(seed >> 32);
+    d.g.rk = dct::make_round_keys(d.g.k0, d.g.k1);
     d.g.first_event = first_event;
     d.g.n_traces = (uint64_t)n_events * (uint64_t)h->p.P;
     d.g.adc = nullptr; d.g.sig_time = nullptr; d.g.sig_charge = nullptr; d.g.table_in_smem = 0;

@@ -39,15 +39,24 @@ __global__ void k_dump_pe(const DumpArgs d) {
             float elapsed = 0.0f;
             int cell = p.cell0;
             float off = p.off0;
-            for (uint32_t i = 0;; ++i) {
-                const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                elapsed += gap;
-                if (elapsed >= p.span) break;
-                advance_onset(p, gap, cell, off);
-                const float A = nsb_amplitude(r, q);
-                // onset coordinate s = cell*dt + off = (time - t0) + x_lo
-                emit((double)cell * p.dt_d + (double)off + p.t0_d - p.x_lo_d, A);
+            for (uint32_t grp_i = 0;; ++grp_i) {
+                const NsbGroup grp = draw_nsb_group(a.rk, t.key, grp_i);
+                const uint32_t gw[4] = {grp.gap.x, grp.gap.y, grp.gap.z, grp.gap.w};
+                const uint32_t bw[4] = {grp.bor.x, grp.bor.y, grp.bor.z, grp.bor.w};
+                float z[4];
+                normal_pair(grp.nrm.x, grp.nrm.y, z[0], z[1]);
+                normal_pair(grp.nrm.z, grp.nrm.w, z[2], z[3]);
+                bool done = false;
+                for (int k = 0; k < 4 && !done; ++k) {
+                    const float gap = exp_gap(gw[k], q.neg_ln2_over_rate);
+                    elapsed += gap;
+                    if (elapsed >= p.span) { done = true; break; }
+                    advance_onset(p, gap, cell, off);
+                    const float A = cluster_amplitude((float)borel(bw[k], q.xt, q.borel_cdf), z[k], q.sigma1);
+                    // onset coordinate s = cell*dt + off = (time - t0) + x_lo
+                    emit((double)cell * p.dt_d + (double)off + p.t0_d - p.x_lo_d, A);
+                }
+                if (done) break;
             }
         } else {
             const float lam = rate * p.dt, p0 = __expf(-lam);

@@ -62,6 +62,7 @@ __device__ __forceinline__ int digitise(float acc, float gain, float z, float si
 struct GenArgs {
     DevParams p;
     uint32_t k0, k1;            // seed
+    RoundKeys rk;               // its Philox key schedule (make_round_keys(k0, k1))
     uint64_t first_event;
     uint64_t n_traces;          // n_events * P
     int16_t* adc;
@@ -141,11 +142,28 @@ struct PixelNsb {
     float sigma1;              // relative gain spread
 };
 
-// One NSB photo-electron cluster from its Philox block: amplitude after crosstalk (:297-327) and
-// gain smearing (:329-348):  A = n + sigma_1 sqrt(n) z.
-__device__ __forceinline__ float nsb_amplitude(const u32x4& r, const PixelNsb& q) {
-    const float fn = (float)borel(r.y, q.xt, q.borel_cdf);
-    return __fmaf_rn(q.sigma1, normal_scaled(r.z, r.w, fn), fn);
+// Random numbers of the continuous NSB stream: four photo-electron clusters per three Philox
+// blocks (pe 4g .. 4g+3 of a trace <-> blocks 3g, 3g+1, 3g+2 of STREAM_NSB):
+//   block 3g     .x .y .z .w -> exponential gap before pe 4g .. 4g+3            (generate_nsb :244-250)
+//   block 3g + 1 .x .y .z .w -> Borel cluster size of pe 4g .. 4g+3            (crosstalk :297-327)
+//   block 3g + 2 (.x, .y)    -> Box-Muller (radius, angle): cos -> pe 4g, sin -> pe 4g+1
+//                (.z, .w)    -> the same for pe 4g+2 and 4g+3                 (gain smearing :329-348)
+// Both normals of a Box-Muller pair are used (they are independent), so a cluster costs three random
+// words instead of four, and half a logarithm / square root instead of one.
+struct NsbGroup { u32x4 gap, bor, nrm; };
+
+__device__ __forceinline__ NsbGroup draw_nsb_group(const RoundKeys& rk, const StreamKey& key, uint32_t g) {
+    NsbGroup n;
+    n.gap = draw_block_rk(rk, key, STREAM_NSB, 3u * g);
+    n.bor = draw_block_rk(rk, key, STREAM_NSB, 3u * g + 1u);
+    n.nrm = draw_block_rk(rk, key, STREAM_NSB, 3u * g + 2u);
+    return n;
+}
+
+// Amplitude of a cluster of fn pe after gain smearing (:329-348):  A = n + sigma_1 sqrt(n) z.
+// One definition for every kernel: they must agree bit for bit.
+__device__ __forceinline__ float cluster_amplitude(float fn, float z, float sigma1) {
+    return __fmaf_rn(sigma1, fast_sqrt(fn) * z, fn);
 }
 
 __device__ __forceinline__ float smeared_amplitude(int n, float z, float sigma1) {
@@ -251,7 +269,7 @@ __device__ __forceinline__ void add_signal_pulses(const GenArgs& a, const TraceI
 // Electronic noise (kept bins only) + digitisation of one trace, in place: the int16 results are
 // packed into the front of the trace's own float row (sample b -> half-word b).  Reading runs
 // ahead of writing (word b/2 <= b), so nothing unread is overwritten.
-__device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId& t, float* row) {
+__device__ __forceinline__ void digitise_trace(const DevParams& p, const RoundKeys& rk, const TraceId& t, float* row) {
     const float gain = p.gain[t.pixel];
     const float sigma_e = p.sigma_e[t.pixel];
     const float baseline = p.baseline[t.pixel];
@@ -263,7 +281,7 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId
     for (int q = 0; q < n_full; ++q) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (sigma_e > 0.0f) {
-            const u32x4 r = draw_block(t.key, STREAM_NOISE, (uint32_t)q);
+            const u32x4 r = draw_block_rk(rk, t.key, STREAM_NOISE, (uint32_t)q);
             normal_pair(r.x, r.y, z[0], z[1]);
             normal_pair(r.z, r.w, z[2], z[3]);
         }
@@ -277,7 +295,7 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const TraceId
         const int q = n_full, b = 4 * n_full;
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (sigma_e > 0.0f) {
-            const u32x4 r = draw_block(t.key, STREAM_NOISE, (uint32_t)q);
+            const u32x4 r = draw_block_rk(rk, t.key, STREAM_NOISE, (uint32_t)q);
             normal_pair(r.x, r.y, z[0], z[1]);
             normal_pair(r.z, r.w, z[2], z[3]);
         }
@@ -377,26 +395,37 @@ k_generate_scatter(const GenArgs a) {
                 float elapsed = 0.0f;
                 int cell = p.cell0;
                 float off = p.off0;                                   // onset = cell*dt + off
-                for (uint32_t i = 0;; ++i) {
-                    const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                    const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                    elapsed += gap;
-                    if (elapsed >= p.span) break;
-                    advance_onset(p, gap, cell, off);
-                    const float A = nsb_amplitude(r, q);
-                    const float x0 = p.dt - off;                      // (0, dt]
-                    if (POLY) {
-                        int f; float u;
-                        phase_of(p, x0, f, u);
-                        const int kb = cell + 1 - p.n_drop;           // kept index of tap 0
-                        const int j_hi = min(p.n_taps, B - kb);
-                        for (int j = max(0, -kb); j < j_hi; ++j)
-                            row[kb + j] = __fmaf_rn(A, horner(tab_s[j * p.n_phase + f], u), row[kb + j]);
-                    } else {
-                        // bin cell+1 sees y = x0.  A pe exactly on a sample is also seen by that
-                        // sample at y = 0: probability ~2^-24 per pe, ignored by both kernels.
-                        scatter_generic(p, coef_g, row, cell + 1, x0, A);
+                for (uint32_t g = 0;; ++g) {
+                    const NsbGroup grp = draw_nsb_group(a.rk, t.key, g);
+                    const uint32_t gw[4] = {grp.gap.x, grp.gap.y, grp.gap.z, grp.gap.w};
+                    const uint32_t bw[4] = {grp.bor.x, grp.bor.y, grp.bor.z, grp.bor.w};
+                    float z[4];
+                    normal_pair(grp.nrm.x, grp.nrm.y, z[0], z[1]);
+                    normal_pair(grp.nrm.z, grp.nrm.w, z[2], z[3]);
+                    bool done = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (done) continue;
+                        const float gap = exp_gap(gw[k], q.neg_ln2_over_rate);
+                        elapsed += gap;
+                        if (elapsed >= p.span) { done = true; continue; }
+                        advance_onset(p, gap, cell, off);
+                        const float A = cluster_amplitude((float)borel(bw[k], q.xt, q.borel_cdf), z[k], q.sigma1);
+                        const float x0 = p.dt - off;                      // (0, dt]
+                        if (POLY) {
+                            int f; float u;
+                            phase_of(p, x0, f, u);
+                            const int kb = cell + 1 - p.n_drop;           // kept index of tap 0
+                            const int j_hi = min(p.n_taps, B - kb);
+                            for (int j = max(0, -kb); j < j_hi; ++j)
+                                row[kb + j] = __fmaf_rn(A, horner(tab_s[j * p.n_phase + f], u), row[kb + j]);
+                        } else {
+                            // bin cell+1 sees y = x0.  A pe exactly on a sample is also seen by that
+                            // sample at y = 0: probability ~2^-24 per pe, ignored by both kernels.
+                            scatter_generic(p, coef_g, row, cell + 1, x0, A);
+                        }
                     }
+                    if (done) break;
                 }
             } else {
                 // on-grid NSB (:259-267): n ~ Poisson(rate dt) pe exactly on every simulated bin
@@ -414,7 +443,7 @@ k_generate_scatter(const GenArgs a) {
         }
         add_signal_pulses(a, t, POLY ? p.coef32 : coef_g, row, q.xt, q.sigma1);
         dump_analog(a, t.g, row);
-        digitise_trace(p, t, row);
+        digitise_trace(p, a.rk, t, row);
     }
     __syncthreads();
     if (a.st.adc_hist)

@@ -77,7 +77,7 @@ k_generate_grid(const GridArgs ga) {
             // what is left in the window belongs to bins past the end of the trace
         }
         add_signal_pulses(a, t, p.coef32, row, q.xt, q.sigma1);
-        digitise_trace(p, t, row);
+        digitise_trace(p, a.rk, t, row);
     }
     __syncthreads();
     if (a.st.adc_hist)

@@ -31,21 +31,12 @@ constexpr int SWEEP_MAX_BINS = 256;
 #ifndef DCT_SWEEP_GROUP
 #define DCT_SWEEP_GROUP 4
 #endif
-#ifndef DCT_SWEEP_UNROLL2
-#define DCT_SWEEP_UNROLL2 1
-#endif
-#ifndef DCT_SWEEP_HOIST_KEYS
-#define DCT_SWEEP_HOIST_KEYS 0
-#endif
 // cost-attribution experiments (profiles/r01/cost_attribution.txt); all produce WRONG cubes
 #ifndef DCT_EXP_NO_SLIDE
 #define DCT_EXP_NO_SLIDE 0
 #endif
 #ifndef DCT_EXP_NO_TAPS
 #define DCT_EXP_NO_TAPS 0
-#endif
-#ifndef DCT_EXP_CHEAP_RNG
-#define DCT_EXP_CHEAP_RNG 0
 #endif
 #ifndef DCT_SWEEP_SKIP
 #define DCT_SWEEP_SKIP 0      // 1: skip tap groups no lane of the warp needs (REDUX min / max of the cell); measured slower once the taps became FFMA2
@@ -138,7 +129,7 @@ k_generate_sweep(const GenArgs a) {
             const int last_needed = p.n_drop + B - 1;        //             and j <  last_needed  - cell
 #endif
             // One photo-electron: slide the window to its cell, then add its taps.
-            auto add_pe = [&](const u32x4& r, float gap) {
+            auto add_pe = [&](float gap, float A) {
                 int kb = cell + kb_shift;
                 int k = advance_onset(p, gap, cell, off);
                 // slide by one cell: predicated, all lanes
@@ -164,7 +155,6 @@ k_generate_sweep(const GenArgs a) {
                         }
                     }
                 }
-                const float A = nsb_amplitude(r, q);
                 int f; float u;
                 phase_of(p, p.dt - off, f, u);
                 const float4* tlo = tab_s + f;
@@ -202,48 +192,29 @@ k_generate_sweep(const GenArgs a) {
                 W[0] += A * u + (float)(j_lo + j_hi) + tlo[0].x + thi[0].x + uu.x + AA.y;   // keep the inputs alive
 #endif
             };
-#if DCT_SWEEP_HOIST_KEYS
-            const PhiloxKeys ks = philox_keys(t.key.k0, t.key.k1);
-            u32x4 ctr;
-            ctr.y = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu); ctr.z = t.key.pixel; ctr.w = t.key.ev_lo;
-            auto draw_nsb = [&](uint32_t i) { u32x4 c = ctr; c.x = i; return philox4x32_keyed(c, ks); };
-#else
-#if DCT_EXP_CHEAP_RNG
-            // COST-ATTRIBUTION EXPERIMENT ONLY (wrong statistics): a 4-multiply hash instead of Philox
-            auto draw_nsb = [&](uint32_t i) {
-                u32x4 c;
-                const uint32_t h = (i + 1u) * 0x9E3779B9u ^ t.key.pixel * 0x85EBCA6Bu ^ t.key.ev_lo * 0xC2B2AE35u;
-                c.x = h * 0xD2511F53u; c.y = (h ^ (h >> 15)) * 0xCD9E8D57u; c.z = (h ^ (h >> 13)) * 0x27D4EB2Fu; c.w = (h ^ (h >> 16)) * 0x165667B1u;
-                return c;
-            };
-#else
-            auto draw_nsb = [&](uint32_t i) { return draw_block(t.key, STREAM_NSB, i); };
-#endif
-#endif
-#if DCT_SWEEP_UNROLL2
-            // two photo-electrons per iteration: their Philox blocks and samplers are independent
-            // and overlap; the window updates stay in order
-            for (uint32_t i = 0;; i += 2) {
-                const u32x4 ra = draw_nsb(i);
-                const u32x4 rb = draw_nsb(i + 1);
-                const float gap_a = exp_gap(ra.x, q.neg_ln2_over_rate);
-                const float gap_b = exp_gap(rb.x, q.neg_ln2_over_rate);
-                elapsed += gap_a;
-                if (elapsed >= p.span) break;
-                add_pe(ra, gap_a);
-                elapsed += gap_b;
-                if (elapsed >= p.span) break;
-                add_pe(rb, gap_b);
+            // Four photo-electrons per three Philox blocks (NsbGroup), two per pass of the inner loop:
+            // their samplers are independent and overlap; the window updates stay in order.
+            bool more = true;
+            for (uint32_t g = 0; more; ++g) {
+                const NsbGroup grp = draw_nsb_group(a.rk, t.key, g);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ga = h ? grp.gap.z : grp.gap.x, gb = h ? grp.gap.w : grp.gap.y;
+                    const uint32_t ba = h ? grp.bor.z : grp.bor.x, bb = h ? grp.bor.w : grp.bor.y;
+                    float za, zb;
+                    normal_pair(h ? grp.nrm.z : grp.nrm.x, h ? grp.nrm.w : grp.nrm.y, za, zb);
+                    const float gap_a = exp_gap(ga, q.neg_ln2_over_rate);
+                    const float gap_b = exp_gap(gb, q.neg_ln2_over_rate);
+                    const float A_a = cluster_amplitude((float)borel(ba, q.xt, q.borel_cdf), za, q.sigma1);
+                    const float A_b = cluster_amplitude((float)borel(bb, q.xt, q.borel_cdf), zb, q.sigma1);
+                    elapsed += gap_a;
+                    if (elapsed >= p.span) { more = false; break; }
+                    add_pe(gap_a, A_a);
+                    elapsed += gap_b;
+                    if (elapsed >= p.span) { more = false; break; }
+                    add_pe(gap_b, A_b);
+                }
             }
-#else
-            for (uint32_t i = 0;; ++i) {
-                const u32x4 r = draw_block(t.key, STREAM_NSB, i);
-                const float gap = exp_gap(r.x, q.neg_ln2_over_rate);
-                elapsed += gap;
-                if (elapsed >= p.span) break;
-                add_pe(r, gap);
-            }
-#endif
             // retire what is left in the window
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
@@ -253,7 +224,7 @@ k_generate_sweep(const GenArgs a) {
         }
         add_signal_pulses(a, t, p.coef32, row, q.xt, q.sigma1);
         dump_analog(a, t.g, row);
-        digitise_trace(p, t, row);
+        digitise_trace(p, a.rk, t, row);
     }
     __syncthreads();
     if (a.st.adc_hist)

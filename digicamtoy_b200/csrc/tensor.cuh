@@ -13,7 +13,7 @@
 // multiplies and one 8-byte shared-memory store per pe -- no per-tap loads or FMAs, no window.
 //
 // The photo-electron stream is the one of the sweep / scatter kernels, Philox block for Philox
-// block (same advance_onset, phase_of, nsb_amplitude), so dct_trace_pe describes this kernel too;
+// block (NsbGroup: same gaps, cluster sizes and amplitudes), so dct_trace_pe describes this kernel too;
 // only the summation differs: moments are rounded to fp16 (11 significant bits, round to nearest,
 // unbiased) before the product, the coefficients are split hi + lo (22 bits), accumulation is
 // fp32.  The analog sum differs from the fp32 kernels by ~2e-3 LSB rms at 1 GHz
@@ -56,14 +56,17 @@ constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #ifndef DCT_TC_POLL_NS
 #define DCT_TC_POLL_NS 1000                    // longest the MMA warp sleeps before it looks at the producers' positions by itself
 #endif
-#ifndef DCT_TC_UNROLL
-#define DCT_TC_UNROLL 4                        // photo-electrons per lane between two looks at the ring state
+#ifndef DCT_TC_REFRESH_LIMIT
+#define DCT_TC_REFRESH_LIMIT 0                 // 1: look at the released-cell counter before every store, not once per group
 #endif
-// mean pe per trace from which AUTO prefers this kernel over the sweep kernel.  1e30 = never:
-// measured on C4 (245 pe / trace) the first version needs 84 ms per 16384 events against the
-// sweep kernel's 60 ms (profiles/r02/tensor_v1.txt), so it is opt-in (kernel='tensor') for now.
+#ifndef DCT_TC_UNROLL
+#define DCT_TC_UNROLL 4                        // (the producer loop now works in groups of four pe: one NsbGroup per look at the ring state)
+#endif
+// mean pe per trace from which AUTO prefers this kernel over the sweep kernel: measured crossover
+// at ~60 pe / trace (0.25 GHz on the 240 ns window; profiles/r02/crossover_tensor.txt) -- below it the
+// per-cell hand-over (59 cells whatever the rate) costs more than the taps it saves.
 #ifndef DCT_TC_MIN_MEAN_PE
-#define DCT_TC_MIN_MEAN_PE 1e30
+#define DCT_TC_MIN_MEAN_PE 70.0
 #endif
 
 struct TensorArgs {
@@ -78,7 +81,6 @@ struct TensorArgs {
     float v_scale;               // 2 / knot_dx
     int check_span;              // 0: the cell test alone ends the pe stream (see k_generate_tensor)
     float y0, y_end;             // producer clock in knot steps from the start of cell0: first value, end of the stream
-    uint32_t rk[2 * DCT_PHILOX_ROUNDS];   // Philox round keys of the seed: (k0 + r W0, k1 + r W1), r = 0 .. ROUNDS-1
 };
 
 // Byte offset of element (row, k) in a canonical K-major, no-swizzle UMMA operand tile with
@@ -99,7 +101,7 @@ __host__ __device__ inline size_t tensor_smem_bytes(int B, int ring) {
 #ifndef DCT_TC_PAD_SMEM
 #define DCT_TC_PAD_SMEM 0      // experiment: extra bytes to limit the CTAs per SM
 #endif
-    return (ringb > rows ? ringb : rows) + 4 * TC_G_BYTES + 64 + DCT_TC_PAD_SMEM;
+    return (ringb > rows ? ringb : rows) + 4 * TC_G_BYTES + 64 + 8 * (size_t)ring + DCT_TC_PAD_SMEM;
 }
 
 namespace tc {
@@ -193,41 +195,10 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
 
 }  // namespace tc
 
-// Philox4x32 with the round keys as kernel parameters: the key schedule (k + r W) depends only on
-// the seed, so the XORs take it straight from the constant bank -- no key registers, no adds.
-// Bit-identical to draw_block(key, STREAM_NSB, block).
-__device__ __forceinline__ u32x4 philox_rk(uint32_t block, uint32_t cy, uint32_t cz, uint32_t cw,
-                                           const uint32_t (&rk)[2 * DCT_PHILOX_ROUNDS]) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    u32x4 c;
-    c.x = block; c.y = cy; c.z = cz; c.w = cw;
-#pragma unroll
-    for (int r = 0; r < DCT_PHILOX_ROUNDS; ++r) {
-        const uint64_t p0 = (uint64_t)M0 * c.x;
-        const uint64_t p1 = (uint64_t)M1 * c.z;
-        u32x4 n;
-        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk[2 * r];
-        n.y = (uint32_t)p1;
-        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk[2 * r + 1];
-        n.w = (uint32_t)p0;
-        c = n;
-    }
-    return c;
-}
-
 // CHECK_SPAN: the pe stream ends where the elapsed time passes the NSB window (as in the other
 // kernels).  When the last cell that can reach a kept bin ends a full cell before the window does
 // (C4: cells 0..58 of 60), the cell test alone ends the stream at the same pe or earlier, with
 // nothing lost, and the elapsed time need not be tracked.
-// Borel cluster size as a float; same value as borel(): the first threshold inline, the rest
-// (0.8 % of the draws at xt = 0.08) through the generic sampler.
-__device__ __forceinline__ float borel_f(uint32_t r, float mu, const float4 cdf) {
-    const float u = u01_open1(r);
-    float fn = u >= cdf.x ? 2.0f : 1.0f;
-    if (u >= cdf.y) fn = (float)borel(r, mu, cdf);
-    return fn;
-}
-
 template <int RING, bool CHECK_SPAN>
 __global__ void __launch_bounds__(TC_THREADS, DCT_TC_MIN_BLOCKS)
 k_generate_tensor(const __grid_constant__ TensorArgs ta) {
@@ -244,14 +215,14 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
     unsigned char* ring = smem_raw;                                   // also the float rows of the epilogue
     unsigned char* g_tiles = smem_raw + (ring_bytes > rows_bytes ? ring_bytes : rows_bytes);   // hi, lo, hi', lo'
     uint32_t* ctl = reinterpret_cast<uint32_t*>(g_tiles + 4 * TC_G_BYTES);
-    // ctl[0..3]: cell every lane of producer warp w has reached; ctl[4]: cells released by the MMA
-    // warp; ctl[5]: TMEM base; ctl[8..9]: mbarrier the MMAs commit to; ctl[10..11]: mbarrier a
-    // producer warp flips whenever it publishes a new position (wakes the MMA warp)
+    // ctl[0..3]: cell every lane of producer warp w has reached; ctl[4]: cells released; ctl[5]: TMEM
+    // base; ctl[10..11]: mbarrier a producer warp flips whenever it publishes a new position (wakes
+    // the MMA warp); ctl[16 ..]: one mbarrier per ring slot that the MMAs of its cell commit to
     uint32_t* warp_pos = ctl;
     uint32_t* released = ctl + 4;
     uint32_t* tmem_slot = ctl + 5;
-    const uint32_t bar = tc::smem_u32(ctl + 8);
     const uint32_t notify = tc::smem_u32(ctl + 10);
+    const uint32_t done = tc::smem_u32(ctl + 16);          // RING mbarriers (8 bytes each): MMAs of the slot's cell done
 
     // ---- one-time setup
     {
@@ -261,8 +232,8 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         for (int i = tid; i < (int)(ring_bytes / 16); i += TC_THREADS) r4[i] = make_int4(0, 0, 0, 0);
         if (tid < 5) ctl[tid] = 0;          // not ctl[5]: tcgen05.alloc (warp 4) writes it concurrently
         if (tid == 0) {
-            tc::mbar_init(bar, 1);
             tc::mbar_init(notify, 1);          // every arrival completes a phase
+            for (int i = 0; i < RING; ++i) tc::mbar_init(done + 8u * (uint32_t)i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -292,18 +263,19 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
     const uint64_t trace0 = (uint64_t)blockIdx.x * TC_TRACES;
 
     if (warp >= 4) {
-        // ================= helper warps: warp 4 issues the MMAs, all four clear consumed slots.
-        // Warps 5-7 only ever wait at hardware barriers (no issue slots); warp 4 polls with sleeps.
+        // ================= helper warps.  Warp 4 issues the MMAs of a cell as soon as every producer
+        // warp is past it (it sleeps on the notify barrier in between); warp 5 waits for the MMAs of
+        // each cell (tcgen05.commit -> done[slot]), clears the slot and releases it.  The two run
+        // independently, so the hand-over of cell c+1 does not queue behind the clearing of cell c.
+        // Warps 6-7 only exist so that the CTA has a multiple of four warps (TMEM lane rule).
         const uint32_t ring_addr = tc::smem_u32(ring);
         const uint32_t g_addr = tc::smem_u32(g_tiles);
-        int slot_i = 0;
-        uint32_t notify_parity = 0;
-        for (int c = 0; c < n_cells; ++c) {
-            const uint32_t slot = ring_addr + (uint32_t)slot_i * TC_SLOT_BYTES;
-            if (warp == 4) {
-                // wait until every producer warp is past cell c: sleep on the notify barrier (a
-                // producer flips it with every new position).  A stale parity only costs one more
-                // look, a missed flip at most DCT_TC_POLL_NS.
+        if (warp == 4) {
+            int slot_i = 0;
+            uint32_t notify_parity = 0;
+            for (int c = 0; c < n_cells; ++c) {
+                const uint32_t slot = ring_addr + (uint32_t)slot_i * TC_SLOT_BYTES;
+                // A stale parity only costs one more look, a missed flip at most DCT_TC_POLL_NS.
                 uint32_t spins = 0;
                 while (true) {
                     const uint32_t m = min(min(tc::ld_volatile(warp_pos), tc::ld_volatile(warp_pos + 1)),
@@ -323,23 +295,27 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     tc::mma_f16(d, a1, tc::smem_desc(g + 256), 1u);
                     tc::mma_f16(d, a0, tc::smem_desc(g + TC_G_BYTES), 1u);
                     tc::mma_f16(d, a1, tc::smem_desc(g + TC_G_BYTES + 256), 1u);
-                    tc::mma_commit(bar);
+                    tc::mma_commit(done + 8u * (uint32_t)slot_i);
                 }
                 __syncwarp();
-                tc::mbar_wait(bar, (uint32_t)(c & 1));
+                if (++slot_i == RING) slot_i = 0;
             }
-            if (c + RING < n_cells) {
-                // the slot will be used again: clear it (generic writes after the async reads finished)
-                asm volatile("bar.sync 2, 128;" ::: "memory");     // MMAs of cell c done (warp 4 saw the mbarrier flip)
-                int4* s4 = reinterpret_cast<int4*>(ring + (size_t)slot_i * TC_SLOT_BYTES);
-                const int h = tid - 128;                       // 128 helper threads x 4 x 16 B = 8 KiB
+        } else if (warp == 5) {
+            int slot_i = 0;
+            uint32_t parity = 0;
+            for (int c = 0; c < n_cells; ++c) {
+                tc::mbar_wait(done + 8u * (uint32_t)slot_i, parity);          // the MMAs of cell c have read the slot
+                if (c + RING < n_cells) {
+                    // the slot will be used again: clear it (generic writes after the async reads finished)
+                    int4* s4 = reinterpret_cast<int4*>(ring + (size_t)slot_i * TC_SLOT_BYTES);
 #pragma unroll
-                for (int i = 0; i < TC_SLOT_BYTES / 16 / 128; ++i) s4[i * 128 + h] = make_int4(0, 0, 0, 0);
-                tc::fence_async_proxy();
-                asm volatile("bar.sync 2, 128;" ::: "memory");     // all helpers: slot cleared
+                    for (int i = 0; i < TC_SLOT_BYTES / 16 / 32; ++i) s4[i * 32 + lane] = make_int4(0, 0, 0, 0);
+                    tc::fence_async_proxy();
+                    __syncwarp();
+                }
+                if (lane == 0) tc::st_volatile(released, (uint32_t)(c + 1));
+                if (++slot_i == RING) { slot_i = 0; parity ^= 1u; }
             }
-            if (tid == 128) tc::st_volatile(released, (uint32_t)(c + 1));
-            if (++slot_i == RING) slot_i = 0;
         }
     } else {
         // ================= producer warps: thread = trace
@@ -357,64 +333,91 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         // row offset of this trace inside a slot (K-major core matrices, see tc_tile_offset)
         uint32_t row_off = tc::smem_u32(ring) + (uint32_t)((tid >> 3) * 512 + (tid & 7) * 16);
         asm volatile("" : "+r"(row_off));                // keep it in a register (ptxas rebuilt it per pe)
-        const uint32_t cy = (STREAM_NSB << 24) | (t.key.ev_hi & 0x00FFFFFFu), cz = t.key.pixel, cw = t.key.ev_lo;
+        auto nsb_block = [&](uint32_t block) { return draw_block_rk(a.rk, t.key, STREAM_NSB, block); };
         const uint32_t n8 = (uint32_t)n_cells * TC_PHASES;
 
-        // Lane state: gi = knot interval of the last pe generated (8 cell + j); pend = that pe still
-        // waits for its ring slot.  A lane whose stream has ended holds gi >= n8 with pend set for
-        // good (the write limit never exceeds n8), so "finished" needs no flag of its own.
+        // Lane state: a queue of the four pe of one NsbGroup (knot interval gq = 8 cell + j, amplitude,
+        // offset), nq = the next one to store (4: queue empty, draw the next group).  A pe past the end
+        // of the stream carries gq >= n8 and is never stored (the write limit never exceeds n8), so a
+        // finished lane simply keeps its queue.
         float y = ta.y0;
-        uint32_t gi = (rate > 0.0f) ? 0u : n8;
-        int pend = (rate > 0.0f) ? 0 : 1;
+        uint32_t gq0 = n8, gq1 = n8, gq2 = n8, gq3 = n8;
+        float Aq0 = 0.f, Aq1 = 0.f, Aq2 = 0.f, Aq3 = 0.f, vq0 = 0.f, vq1 = 0.f, vq2 = 0.f, vq3 = 0.f;
+        int nq = (rate > 0.0f) ? 4 : 0;
+        uint32_t cur8 = (rate > 0.0f) ? 0u : n8;         // 8 x the cell this lane has reached
+        uint32_t prev = 0xffffffffu;                     // interval of the last pe of the group before
         uint32_t warp_done = 0;
         uint32_t limit8 = min((uint32_t)RING * TC_PHASES, n8);   // intervals below it may be written: 8 (released + RING)
-        float keep = 0.0f;                               // 1: same (cell, interval) as the pe before -> sums carry on
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        float A = 0.f, v = 0.f;
-        uint32_t i = 0;
+        uint32_t grp = 0;
         uint32_t idle = 0;
-        u32x4 r = philox_rk(0u, cy, cz, cw, ta.rk);
+        const float cdf1 = q.borel_cdf.x, cdf2 = q.borel_cdf.y;
+
+        // one pe of the group: clock, interval, offset, amplitude
+        auto make_pe = [&](uint32_t w_gap, uint32_t w_bor, float z, uint32_t& gq, float& Aq, float& vq) {
+            y = fminf(__fmaf_rn(fast_lg2(u01_open0(w_gap)), gap_scale, y), 4194304.0f);
+            const float yi = __fadd_rz(y, 8388608.0f);              // 2^23 + floor(y)
+            uint32_t g = __float_as_uint(yi) & 0x007fffffu;
+            if (CHECK_SPAN) g = (y < ta.y_end) ? g : 0x00800000u;    // past the NSB window
+            gq = g;
+            vq = __fmaf_rn(y - (yi - 8388608.0f), -2.0f, 1.0f);
+            // Borel cluster size: the first threshold inline, the rest (0.8 % of the draws at
+            // xt = 0.08) through the generic sampler -- same value as borel()
+            const float u = u01_open1(w_bor);
+            float fn = u >= cdf1 ? 2.0f : 1.0f;
+            if (u >= cdf2) fn = (float)borel(w_bor, q.xt, p.borel_cdf[t.pixel]);
+            Aq = cluster_amplitude(fn, z, q.sigma1);
+        };
+        // store pe k of the queue if it is this lane's next one and its slot is free
+        auto store_pe = [&](int k, uint32_t gq, uint32_t before, float A, float v, uint32_t next) {
+#if DCT_TC_REFRESH_LIMIT
+            if (k > 0) limit8 = min((tc::ld_volatile(released) + (uint32_t)RING) * TC_PHASES, n8);
+#endif
+            if (nq == k && gq < limit8) {
+                const float keep = gq == before ? 1.0f : 0.0f;   // same (cell, interval) as the pe before: sums carry on
+                const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
+                acc0 = __fmaf_rn(acc0, keep, A);
+                acc1 = __fmaf_rn(acc1, keep, m1);
+                acc2 = __fmaf_rn(acc2, keep, m2);
+                acc3 = __fmaf_rn(acc3, keep, m3);
+                const __half2 h01 = __floats2half2_rn(acc0, acc1);
+                const __half2 h23 = __floats2half2_rn(acc2, acc3);
+                // slot of the cell + place of interval j in the row: (j >> 1) 128 + (j & 1) 8 bytes,
+                // from a byte table (PRMT) -- {0, 1, 16, 17, 32, 33, 48, 49} x 8
+                const uint32_t joff8 = __byte_perm(0x11100100u, 0x31302120u, gq & 7u);
+                const uint32_t addr = row_off + ((gq >> 3) % (uint32_t)RING) * TC_SLOT_BYTES + (joff8 << 3);
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
+                             :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                                "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+                nq = k + 1;
+                cur8 = next;
+            }
+        };
 
         while (true) {
-#pragma unroll
-            for (int rep = 0; rep < DCT_TC_UNROLL; ++rep) {
-                if (!pend) {
-                    const u32x4 rn = philox_rk(i + 1u, cy, cz, cw, ta.rk);    // independent of r: overlaps
-                    y = fminf(__fmaf_rn(fast_lg2(u01_open0(r.x)), gap_scale, y), 4194304.0f);
-                    const float yi = __fadd_rz(y, 8388608.0f);          // 2^23 + floor(y)
-                    uint32_t g = __float_as_uint(yi) & 0x007fffffu;
-                    if (CHECK_SPAN) g = (y < ta.y_end) ? g : 0x00800000u;  // past the NSB window
-                    const float w = y - (yi - 8388608.0f);
-                    v = __fmaf_rn(w, -2.0f, 1.0f);
-                    const float fn = borel_f(r.y, q.xt, q.borel_cdf);
-                    A = __fmaf_rn(q.sigma1, normal_scaled(r.z, r.w, fn), fn);
-                    keep = g == gi ? 1.0f : 0.0f;
-                    gi = g;
-                    pend = 1;
-                    r = rn;
-                    ++i;
-                }
-                if (pend && gi < limit8) {
-                    const float m1 = A * v, m2 = m1 * v, m3 = m2 * v;
-                    acc0 = __fmaf_rn(acc0, keep, A);
-                    acc1 = __fmaf_rn(acc1, keep, m1);
-                    acc2 = __fmaf_rn(acc2, keep, m2);
-                    acc3 = __fmaf_rn(acc3, keep, m3);
-                    const __half2 h01 = __floats2half2_rn(acc0, acc1);
-                    const __half2 h23 = __floats2half2_rn(acc2, acc3);
-                    // slot of the cell + place of interval j in the row: (j >> 1) 128 + (j & 1) 8 bytes,
-                    // from a byte table (PRMT) -- {0, 1, 16, 17, 32, 33, 48, 49} x 8
-                    const uint32_t cellq = gi >> 3;
-                    const uint32_t joff8 = __byte_perm(0x11100100u, 0x31302120u, gi & 7u);
-                    const uint32_t addr = row_off + (cellq % (uint32_t)RING) * TC_SLOT_BYTES + (joff8 << 3);
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};"
-                                 :: "r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                                    "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
-                    pend = 0;
-                }
+            if (nq == 4) {
+                // queue empty: the next four pe (three Philox blocks: gaps, cluster sizes, two Box-Muller pairs)
+                const u32x4 rg = nsb_block(3u * grp);
+                const u32x4 rb = nsb_block(3u * grp + 1u);
+                const u32x4 rn = nsb_block(3u * grp + 2u);
+                ++grp;
+                float z0, z1, z2, z3;
+                normal_pair(rn.x, rn.y, z0, z1);
+                normal_pair(rn.z, rn.w, z2, z3);
+                prev = gq3;
+                make_pe(rg.x, rb.x, z0, gq0, Aq0, vq0);
+                make_pe(rg.y, rb.y, z1, gq1, Aq1, vq1);
+                make_pe(rg.z, rb.z, z2, gq2, Aq2, vq2);
+                make_pe(rg.w, rb.w, z3, gq3, Aq3, vq3);
+                nq = 0;
+                cur8 = gq0;
             }
+            store_pe(0, gq0, prev, Aq0, vq0, gq1);
+            store_pe(1, gq1, gq0, Aq1, vq1, gq2);
+            store_pe(2, gq2, gq1, Aq2, vq2, gq3);
+            store_pe(3, gq3, gq2, Aq3, vq3, gq3);
             // publish the cell every lane of this warp has reached
-            const uint32_t wmin = __reduce_min_sync(0xffffffffu, gi) >> 3;
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, cur8) >> 3;
             if (wmin > warp_done) {
                 tc::fence_async_proxy();
                 __syncwarp();
@@ -426,7 +429,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             }
             if (wmin >= (uint32_t)n_cells) break;
             limit8 = min((tc::ld_volatile(released) + (uint32_t)RING) * TC_PHASES, n8);
-            if (!__any_sync(0xffffffffu, !pend || gi < limit8)) {      // every lane waits for a slot
+            if (!__any_sync(0xffffffffu, nq == 4 || cur8 < limit8)) {      // every lane waits for a slot
                 __nanosleep(32);
                 if (++idle > (1u << 26)) __trap();       // a protocol error fails the launch instead of hanging
             }
@@ -467,7 +470,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         if (live) {
             const TraceId t = trace_id(a, trace0 + tid);
             dump_analog(a, t.g, row);
-            digitise_trace(p, t, row);
+            digitise_trace(p, a.rk, t, row);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (a.st.adc_hist)

@@ -56,7 +56,7 @@ class NTraceGenerator:
                  voltage_drop=False,
                  # --- additions of this implementation (all optional)
                  seed=None, device=None, batch_events=None, saturate=(0, 4095), verbose=False,
-                 kernel='auto', first_event=0,
+                 kernel='auto', first_event=0, prefetch=True,
                  **kwargs):  # unknown keys are ignored: produce_data passes its whole option set (:113)
         p = build_params(time_start=time_start, time_end=time_end, time_sampling=time_sampling,
                          n_pixels=n_pixels, nsb_rate=nsb_rate, crosstalk=crosstalk, gain_nsb=gain_nsb,
@@ -106,7 +106,11 @@ class NTraceGenerator:
             # ~32 MiB of ADC per batch keeps the per-event iterator responsive
             batch_events = max(1, min(4096, (32 << 20) // (p.n_pixels * p.n_bins * 2)))
         self.batch_events = int(batch_events)
-        self._host = None          # pinned (adc, time, charge) of the current batch
+        self._host = None          # (adc, time, charge) views of the current batch
+        self._bufs = [None, None]  # the two pinned batch slots of the iterator
+        self._prefetch = None      # (first event, slot, future) of the batch being generated ahead
+        self._pool = None
+        self.prefetch = bool(prefetch)
         self._batch_first = 0      # event index (relative) of slot 0 of the current batch
         self._batch_len = 0
         self.reset()
@@ -255,6 +259,8 @@ class NTraceGenerator:
         if truth:
             t = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory()
             q = torch.empty((n_events, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory()
+        if self._prefetch is not None:                   # the host pipeline of a handle serves one call at a time
+            self._prefetch[2].result()
         if n_events:
             self._handle.generate_host(self.seed, int(first_event), n_events, adc.data_ptr(),
                                        t.data_ptr() if truth else None,
@@ -266,13 +272,73 @@ class NTraceGenerator:
         return (a, t.numpy(), q.numpy()) if truth else a
 
     # ------------------------------------------------------------------ internals
-    def _fill_batch(self, first_relative):
+    def _batch_buffers(self, which):
+        """Pinned (adc, time, charge) tensors of iterator batch slot `which` (0 / 1), allocated once."""
+        torch = _torch()
+        if self._bufs[which] is None:
+            p, n = self.params, self.batch_events
+            self._bufs[which] = (torch.empty((n, p.n_pixels, p.n_bins), dtype=torch.int16).pin_memory(),
+                                 torch.empty((n, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory(),
+                                 torch.empty((n, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory())
+        return self._bufs[which]
+
+    def _generate_batch(self, which, first_relative, n):
+        """Batch [first_relative, +n) into slot `which`; returns NumPy views like generate_host."""
+        adc, t, q = self._batch_buffers(which)
+        self._handle.generate_host(self.seed, self.first_event + first_relative, n, adc.data_ptr(),
+                                   t.data_ptr(), q.data_ptr())
+        a = adc.numpy()[:n]
+        if self.saturate[0] >= 0:
+            a = a.view(np.uint16)
+        return a, t.numpy()[:n], q.numpy()[:n]
+
+    def _batch_size_at(self, first_relative):
         n = self.batch_events
         if self.n_events is not None:
-            n = min(n, self.n_events - first_relative)
-        self._host = self.generate_host(n, first_event=self.first_event + first_relative)
+            n = max(0, min(n, self.n_events - first_relative))
+        return n
+
+    def _fill_batch(self, first_relative):
+        """The iterator's batch that starts at event `first_relative`: two pinned slots, reused; while
+        the caller walks through one, the next batch is generated and copied into the other on a
+        worker thread (the C call releases the GIL).  The per-event arrays the iterator hands out are
+        views into a slot and stay valid until that slot is refilled, one full batch later."""
+        n = self._batch_size_at(first_relative)
+        pending = self._prefetch
+        self._prefetch = None
+        if pending is not None and pending[0] == first_relative:
+            which, host = pending[1], pending[2].result()
+        else:
+            if pending is not None:
+                pending[2].result()                      # never two calls on one handle at a time
+            which = 0
+            host = self._generate_batch(which, first_relative, n)
+        self._host = host
         self._batch_first = first_relative
         self._batch_len = n
+        nxt = first_relative + n
+        n_next = self._batch_size_at(nxt)
+        if n_next > 0 and self.prefetch:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=1)
+            self._prefetch = (nxt, 1 - which, self._pool.submit(self._generate_batch, 1 - which, nxt, n_next))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def close(self):
-        self._handle.close()
+        if getattr(self, '_prefetch', None) is not None:
+            try:
+                self._prefetch[2].result()
+            except Exception:
+                pass
+            self._prefetch = None
+        if getattr(self, '_pool', None) is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        if getattr(self, '_handle', None) is not None:
+            self._handle.close()

@@ -33,7 +33,7 @@ def test_b200_arm_json_line():
     assert r['achieved'] > 5 and r['traffic'] is not None
     e = j['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 2048 * 1296 * 50 * 2
-    assert j['gpu_launches'] == 3 and j['value'] > 1e9            # one fused generation + statistics kernel per step
+    assert j['gpu_launches'] == 6 and j['value'] > 1e9            # generation + statistics kernel per step
     assert set(j['config']) == {'workload', 'n_pixels', 'n_bins'}
     assert j['validation']['n_events_reduced'] == 3 * 2048
     assert 300 < j['validation']['mean_adc'] < 500

@@ -26,7 +26,7 @@ def test_c4_full_camera_moments_and_spectrum_against_oracle():
     from digicamtoy_b200.stats import CubeStats
     kw = workloads.c4_full_camera()
     g = _gen(seed=workloads.C4_SEED, **kw)
-    assert g.kernel == 'sweep'
+    assert g.kernel == 'tensor'           # auto: 245 pe / trace is above the tensor kernel's crossover (~60)
     n_events = 4096
     cube = g.generate(n_events)
     st = CubeStats(g)
@@ -70,7 +70,7 @@ def test_dark_yaml_full_camera_against_closed_form():
     from digicamtoy_b200 import workloads
     kw = workloads.c1_dark(n_photon=3)
     g = _gen(seed=11, **kw)
-    assert g.kernel == 'sweep'            # auto: the sweep kernel wins at every rate (scripts/kernel_crossover.py)
+    assert g.kernel == 'sweep'            # auto: 1.2 pe / trace, far below the tensor kernel's crossover; 92 bins > 80
     c = g.generate(3000).cpu().numpy()
     assert c.shape == (3000, 1296, 92)
     cfg = orc.make_config(**kw)

@@ -371,7 +371,7 @@ def test_twelve_bit_saturation_on_c4():
     P = 1296
     npe = [[float(10 ** (3.5 * i / (P - 1)))] for i in range(P)]
     g = gen(n_pixels=P, nsb_rate=1.0, n_photon=npe, seed=20261019, **ACDC)
-    assert g.kernel == 'sweep'
+    assert g.kernel == 'tensor'                                 # auto-selected at 240 pe / trace
     c = cube(g, 16)
     assert c.min() >= 0 and c.max() == 4095
     peak = c.max(axis=2).mean(axis=0)
@@ -731,6 +731,35 @@ def test_on_grid_mode_high_statistics_against_closed_form(rate, xt):
     z = (mean - want_mean) / np.sqrt(want_var / n)
     assert np.abs(z).max() < 5, z
     assert np.abs(var / want_var - 1).max() < 0.01, (var / want_var)
+
+
+def test_iterator_prefetches_into_two_reused_pinned_batches():
+    """for event in generator (reference produce_data.py:119-126): events come out of two pinned batch
+    slots that are allocated once; the next batch is generated while the current one is consumed;
+    the events are the ones the bulk call gives."""
+    g = gen(n_pixels=33, nsb_rate=0.3, n_photon=4., seed=17, n_events=53, batch_events=10, **ACDC)
+    bulk, t_bulk, q_bulk = cube(gen(n_pixels=33, nsb_rate=0.3, n_photon=4., seed=17, **ACDC), 53, truth=True)
+    slots = set()
+    n = 0
+    for ev in g:
+        assert np.array_equal(np.asarray(ev.adc_count).astype(np.int16), bulk[ev.count])
+        assert np.array_equal(ev.cherenkov_time, t_bulk[ev.count]) and np.array_equal(ev.cherenkov_photon, q_bulk[ev.count])
+        slots.add(g._host[0].ctypes.data)
+        n += 1
+    assert n == 53 and g.count == 52
+    assert len(slots) == 2                                   # batches alternate between the two slots
+    assert {b[0].data_ptr() for b in g._bufs} == slots       # ... which were allocated exactly once
+    # without prefetching: one slot, same events
+    g1 = gen(n_pixels=33, nsb_rate=0.3, n_photon=4., seed=17, n_events=25, batch_events=10, prefetch=False, **ACDC)
+    assert all(np.array_equal(np.asarray(ev.adc_count).astype(np.int16), bulk[ev.count]) for ev in g1)
+    assert g1._bufs[1] is None
+    # a bulk host call in between waits for the batch in flight and does not disturb the iterator
+    g2 = gen(n_pixels=33, nsb_rate=0.3, n_photon=4., seed=17, n_events=30, batch_events=10, **ACDC)
+    next(g2)
+    extra = g2.generate_host(5, first_event=40, truth=False)
+    assert np.array_equal(extra.view(np.int16), bulk[40:45])
+    assert all(np.array_equal(np.asarray(ev.adc_count).astype(np.int16), bulk[ev.count]) for ev in g2)
+    g.close(); g1.close(); g2.close()
 
 
 def test_pe_list_attributes_of_the_iterator():
