@@ -312,6 +312,15 @@ def run_b200_arm(a):
                    d2h_bytes_per_step=E * P * B * 2, steps=n_e2e, ms_per_step=h_ms / n_e2e,
                    api='NTraceGenerator.generate_host -> dct_generate_host (pinned host buffer, chunked D2H overlapped with generation)',
                    host_cpus_rank0=(cpus if isinstance(cpus, str) else '%d cpus: %s..%s' % (len(cpus), cpus[0], cpus[-1])))
+        # what a plain N-way cudaMemcpyAsync D2H of the same bytes sustains on this kind of box
+        # (scripts/host_path.py, profiles/r02/host_path.txt): the ceiling of any end-to-end number
+        cpath = os.path.join(ROOT, 'profiles', 'r02', 'host_path_ceiling.json')
+        if os.path.exists(cpath):
+            ceiling = json.load(open(cpath)).get(str(world))
+            if ceiling:
+                gbps = e2e['value'] * 2 / 1e9
+                e2e.update(GBps=gbps, plain_copy_ceiling_GBps=ceiling, frac_of_ceiling=gbps / ceiling,
+                           bound='host ingest: PCIe link at N = 1, the box\'s aggregate host path beyond (profiles/r02/host_path.txt)')
         del host
     # ---- the reference's own way of consuming the generator: `for event in generator`
     # (reference produce_data.py:119-126), one event at a time out of prefetched pinned batches

@@ -14,31 +14,73 @@ class CubeStats:
 
     def __init__(self, generator, charge_lo=-2048, n_charge_bins=16384):
         import torch
-        self._torch = torch
-        self.gen = generator
         p = generator.params
-        lo, hi = generator.saturate
-        dev = torch.device('cuda', generator.device)
+        self._setup(torch, p.n_pixels, p.n_bins, generator.saturate, np.asarray(p.baseline, dtype=np.float64),
+                    charge_lo, n_charge_bins, torch.device('cuda', generator.device))
+        self.gen = generator
+
+    @classmethod
+    def from_shapes(cls, n_pixels, n_bins, saturate=(0, 4095), baseline=0.0, charge_lo=-2048, n_charge_bins=16384,
+                    device='cpu'):
+        """The accumulator without a generator: same buffers, same all-reduce, same results.  Cubes are
+        added with ``accumulate_numpy`` (host arithmetic) -- for merging statistics files and for
+        exercising the multi-rank reduction on machines without a GPU (gloo)."""
+        import torch
+        self = cls.__new__(cls)
+        self._setup(torch, int(n_pixels), int(n_bins), tuple(saturate),
+                    np.broadcast_to(np.asarray(baseline, dtype=np.float64), (int(n_pixels),)).copy(),
+                    charge_lo, n_charge_bins, torch.device(device))
+        self.gen = None
+        return self
+
+    def _setup(self, torch, n_pixels, n_bins, saturate, baseline, charge_lo, n_charge_bins, dev):
+        self._torch = torch
+        self.n_pixels, self.n_bins, self.saturate, self._baseline = n_pixels, n_bins, saturate, baseline
+        lo, hi = saturate
         self.charge_lo, self.n_charge_bins = int(charge_lo), int(n_charge_bins)
         # one flat float64 + one flat int64 buffer: a sharded run all-reduces exactly two tensors
-        self._f = torch.zeros(2 * p.n_bins + 2 * p.n_pixels + 4, dtype=torch.float64, device=dev)
+        self._f = torch.zeros(2 * n_bins + 2 * n_pixels + 4, dtype=torch.float64, device=dev)
         self._i = torch.zeros((hi - lo + 1) + self.n_charge_bins + 1, dtype=torch.int64, device=dev)
         self._slices_f = {}
         o = 0
-        for name, n in (('bin_sum', p.n_bins), ('bin_sumsq', p.n_bins), ('pixel_sum', p.n_pixels),
-                        ('pixel_sumsq', p.n_pixels), ('moments', 4)):
+        for name, n in (('bin_sum', n_bins), ('bin_sumsq', n_bins), ('pixel_sum', n_pixels),
+                        ('pixel_sumsq', n_pixels), ('moments', 4)):
             self._slices_f[name] = slice(o, o + n)
             o += n
         self._slices_i = {'adc_hist': slice(0, hi - lo + 1),
                           'charge_hist': slice(hi - lo + 1, hi - lo + 1 + self.n_charge_bins),
                           'n_events': slice(hi - lo + 1 + self.n_charge_bins, hi - lo + 2 + self.n_charge_bins)}
-        self.with_charge = p.n_bins <= 128
+        self.with_charge = n_bins <= 128
+
+    def accumulate_numpy(self, cube):
+        """Host-side twin of ``accumulate`` (NumPy arithmetic on a ``[n, P, B]`` integer array): the
+        same quantities into the same buffers.  Not used by the generation path."""
+        torch = self._torch
+        c = np.asarray(cube).astype(np.int64)
+        assert c.ndim == 3 and c.shape[1:] == (self.n_pixels, self.n_bins)
+        lo, hi = self.saturate
+        f = np.zeros(self._f.numel()); i = np.zeros(self._i.numel(), dtype=np.int64)
+        i[self._slices_i['adc_hist']] = np.bincount((c - lo).ravel(), minlength=hi - lo + 1)
+        f[self._slices_f['bin_sum']] = c.sum(axis=(0, 1)); f[self._slices_f['bin_sumsq']] = (c ** 2).sum(axis=(0, 1))
+        f[self._slices_f['pixel_sum']] = c.sum(axis=(0, 2)); f[self._slices_f['pixel_sumsq']] = (c ** 2).sum(axis=(0, 2))
+        x = c.ravel().astype(np.float64)
+        f[self._slices_f['moments']] = [x.sum(), (x ** 2).sum(), (x ** 3).sum(), (x ** 4).sum()]
+        if self.with_charge:
+            base = np.rint(self._baseline.astype(np.float32)).astype(np.int64)
+            charge = c.sum(axis=2) - self.n_bins * base[None, :] - self.charge_lo
+            i[self._slices_i['charge_hist']] = np.bincount(np.clip(charge.ravel(), 0, self.n_charge_bins - 1),
+                                                           minlength=self.n_charge_bins)
+        i[self._slices_i['n_events']] = c.shape[0]
+        self._f += torch.from_numpy(f).to(self._f.device)
+        self._i += torch.from_numpy(i).to(self._i.device)
 
     def _ptr(self, buf, sl):
         return buf.data_ptr() + sl.start * buf.element_size()
 
     def accumulate(self, adc, stream=None):
         torch = self._torch
+        if self.gen is None:
+            raise RuntimeError('this accumulator has no generator: use accumulate_numpy')
         p = self.gen.params
         if adc.dtype != torch.int16 or not adc.is_contiguous() or not adc.is_cuda:
             raise ValueError('adc must be a contiguous int16 CUDA tensor')
@@ -100,8 +142,8 @@ class CubeStats:
     def moments_nsb(self):
         """(mean, mean_error, std, std_error) over all samples, as ``compute_moments_nsb``
         defines them (reference nsb_baseline.py:21-32)."""
-        return moments_from_power_sums(self.result()['moments'],
-                                       self.result()['n_events'] * self.gen.params.n_pixels * self.gen.params.n_bins)
+        r = self.result()
+        return moments_from_power_sums(r['moments'], r['n_events'] * self.n_pixels * self.n_bins)
 
 
 def moments_from_power_sums(power_sums, n):

@@ -50,6 +50,52 @@ def test_sharded_statistics_reduce_to_single_process_result(tmp_path):
     assert z['t'][0] == 2.0
 
 
+def _stats_worker(rank, world, port, n_events, out_dir):
+    """The product's own accumulator and its all_reduce (CubeStats), on CPU tensors over gloo: every
+    rank adds the statistics of its shard of one synthetic cube; rank 0 saves the reduced result."""
+    sys.path.insert(0, ROOT)
+    from digicamtoy_b200 import workloads
+    from digicamtoy_b200.stats import CubeStats
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    cube = _synthetic_cube(n_events)
+    first, count = workloads.shard_events(n_events, rank, world)
+    st = CubeStats.from_shapes(7, 10, saturate=(0, 4095), baseline=200.4, charge_lo=-100, n_charge_bins=400)
+    if count:
+        st.accumulate_numpy(cube[first:first + count])
+    st.all_reduce()
+    if rank == 0:
+        r = st.result()
+        np.savez(os.path.join(out_dir, 's.npz'), moments_nsb=np.array(st.moments_nsb()), **r)
+    dist.destroy_process_group()
+
+
+def _synthetic_cube(n_events):
+    rs = np.random.RandomState(5)
+    c = rs.normal(200, 3, size=(n_events, 7, 10)).round().astype(np.int64)
+    c[3, 2, :] = 4095                                                    # a saturated trace: charge beyond the last bin
+    c[4, 1, :] = 0
+    return c
+
+
+def test_cube_stats_all_reduce_over_gloo_equals_the_unsharded_statistics(tmp_path):
+    from digicamtoy_b200.stats import CubeStats
+    n_events, world = 23, 2
+    mp.spawn(_stats_worker, args=(world, _free_port(), n_events, str(tmp_path)), nprocs=world, join=True)
+    z = np.load(tmp_path / 's.npz')
+    whole = CubeStats.from_shapes(7, 10, saturate=(0, 4095), baseline=200.4, charge_lo=-100, n_charge_bins=400)
+    whole.accumulate_numpy(_synthetic_cube(n_events))
+    r = whole.result()
+    assert int(z['n_events']) == n_events == r['n_events']
+    for key in ('adc_hist', 'charge_hist', 'bin_sum', 'bin_sumsq', 'pixel_sum', 'pixel_sumsq'):
+        assert np.array_equal(z[key], r[key]), key
+    assert np.allclose(z['moments'], r['moments'], rtol=1e-14)
+    c = _synthetic_cube(n_events).astype(float)
+    assert z['moments_nsb'][0] == c.mean() and abs(z['moments_nsb'][2] - c.std()) < 1e-9
+    assert r['charge_hist'][-1] == 1 and r['charge_hist'][0] == 1      # the two rail traces, clamped
+
+
 def test_cube_stats_all_reduce_is_noop_without_process_group():
     from digicamtoy_b200.stats import moments_from_power_sums
     x = np.random.RandomState(0).normal(300, 10, 5000).round()

@@ -489,6 +489,14 @@ def _check_stats_against_numpy(g, out, charge_lo, n_charge_bins, pieces=(None,))
         assert np.array_equal(r['charge_hist'], want)
     x = c.ravel().astype(np.float64)
     assert np.allclose(r['moments'], [x.sum(), (x ** 2).sum(), (x ** 3).sum(), (x ** 4).sum()], rtol=1e-12)
+    # the host-side twin used by the gloo test (CubeStats.accumulate_numpy) gives the same buffers
+    if g.saturate == (0, 4095):
+        twin = CubeStats.from_shapes(P, B, saturate=g.saturate, baseline=g.baseline, charge_lo=charge_lo,
+                                     n_charge_bins=n_charge_bins)
+        twin.accumulate_numpy(c)
+        t = twin.result()
+        for key in ('adc_hist', 'bin_sum', 'bin_sumsq', 'pixel_sum', 'pixel_sumsq') + (('charge_hist',) if B <= 128 else ()):
+            assert np.array_equal(t[key], r[key]), key
 
 
 @pytest.mark.parametrize('name,kw,n_events', [

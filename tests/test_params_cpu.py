@@ -88,6 +88,31 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(native.DctConfig) == 160
 
 
+def test_shipped_library_is_sm_100a_and_the_tensor_kernel_uses_tcgen05():
+    """cuobjdump of the in-tree .so (works without a GPU): the only target is sm_100a, the high-rate
+    generation kernel issues tcgen05.mma (SASS UTCHMMA) and commits to mbarriers (UTCBAR), the cube
+    leaves through 16-byte streaming stores, and profiles/r02/sass_evidence.txt describes this build."""
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('no cuobjdump')
+    native.load_library()
+    elf = subprocess.run(['cuobjdump', '-lelf', native.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_\w+', elf))
+    assert archs == {'sm_100a'}, archs
+    sass = subprocess.run(['cuobjdump', '-sass', native.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = re.split(r'Function : ', sass)[1:]
+    by_name = {k.split()[0]: k for k in kernels}
+    tensor = [v for k, v in by_name.items() if 'k_generate_tensor' in k]
+    assert tensor and all('UTCHMMA' in t and 'UTCBAR' in t and 'STG.E.EF.128' in t for t in tensor)
+    sweep = [v for k, v in by_name.items() if 'k_generate_sweep' in k]
+    assert sweep and all('FFMA2' in t for t in sweep)
+    evidence = open(os.path.join(ROOT, 'profiles', 'r02', 'sass_evidence.txt')).read()
+    for name in by_name:                                   # regenerate with scripts/sass_evidence.py after a kernel is added
+        short = re.search(r'dct\d+(k_[a-z_]+?)(I|E)', name)
+        assert short is None or short.group(1) in evidence, name
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
