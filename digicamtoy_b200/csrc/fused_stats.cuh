@@ -55,11 +55,15 @@ __device__ __noinline__ void fs_outside(FsOutside& o, unsigned long long* adc_hi
 // Called by NT threads (tid = threadIdx.x < NT, thread = trace) after every row of the CTA holds
 // its packed int16 samples (sample b -> half-word b of the row) and a barrier has made them
 // visible.  BAR = named barrier of exactly these NT threads.  `smem` = fused_stats_smem(NT, B) bytes.
+// Out of line on purpose: inlined, its registers and code size cost the generation kernels 1-8 % even
+// with the statistics switched off (measured on the grid and sweep kernels).
 template <int NT, int BAR>
-__device__ __forceinline__ void cta_fused_stats(const FusedStats& s, const DevParams& p, uint64_t trace0,
-                                                uint64_t n_traces, const float* rows, unsigned char* smem) {
+__device__ __noinline__ void cta_fused_stats(const FusedStats s, const int B, const int P, const int adc_min,
+                                             const int adc_max, const float* baseline, uint64_t trace0,
+                                             uint64_t n_traces, const float* rows, unsigned char* smem) {
+    // (everything by value: a reference to the kernel's parameter block would move it to local memory)
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int B = p.B, SB = B | 1;
+    const int SB = B | 1;
     unsigned short* priv_all = reinterpret_cast<unsigned short*>(smem);                   // [NT/32][FS_WIN][32]
     unsigned int* hist_s = reinterpret_cast<unsigned int*>(smem + (size_t)NT * FS_WIN * 2);   // [FS_HIST]
     unsigned long long* bin_s = reinterpret_cast<unsigned long long*>(hist_s + FS_HIST);   // [B] sums, [B] sums of squares
@@ -102,14 +106,14 @@ __device__ __forceinline__ void cta_fused_stats(const FusedStats& s, const DevPa
             for (int b = 0; b < B; ++b) {
                 const int v = (int)(short)hw[b];
                 if ((unsigned int)(v - s.win_lo) >= (unsigned int)FS_WIN && (unsigned int)(v - s.hist_lo) >= (unsigned int)FS_HIST)
-                    fs_outside(outside, s.adc_hist, p.adc_min, p.adc_max, v, 1u, true);
+                    fs_outside(outside, s.adc_hist, adc_min, adc_max, v, 1u, true);
             }
         const uint64_t g = trace0 + tid;
-        const int pixel = (int)(g % (uint64_t)p.P);
+        const int pixel = (int)(g % (uint64_t)P);
         atomicAdd(s.pixel_sum + pixel, (double)ts);
         atomicAdd(s.pixel_sumsq + pixel, (double)tq);
         if (s.charge_hist) {
-            const long long bin = ts - (long long)B * llrintf(p.baseline[pixel]) - s.charge_lo;
+            const long long bin = ts - (long long)B * llrintf(baseline[pixel]) - s.charge_lo;
             if (bin >= s.n_charge_bins - 1) ++n_charge_over;
             else if (bin <= 0) ++n_charge_under;
             else atomicAdd(s.charge_hist + bin, 1ull);
@@ -142,7 +146,7 @@ __device__ __forceinline__ void cta_fused_stats(const FusedStats& s, const DevPa
             const int v = s.win_lo + w;
             const unsigned int hs = (unsigned int)(v - s.hist_lo);
             if (hs < (unsigned int)FS_HIST) atomicAdd(&hist_s[hs], c);
-            else fs_outside(outside, s.adc_hist, p.adc_min, p.adc_max, v, c, false);
+            else fs_outside(outside, s.adc_hist, adc_min, adc_max, v, c, false);
         }
     }
     if (s.charge_hist) {
@@ -154,17 +158,17 @@ __device__ __forceinline__ void cta_fused_stats(const FusedStats& s, const DevPa
     {
         const unsigned int hi = __reduce_add_sync(0xffffffffu, outside.rail_hi);
         const unsigned int lo = __reduce_add_sync(0xffffffffu, outside.rail_lo);
-        if (lane == 0 && hi) fs_outside(outside, s.adc_hist, p.adc_min, p.adc_max, p.adc_max, hi, false);
-        if (lane == 0 && lo) fs_outside(outside, s.adc_hist, p.adc_min, p.adc_max, p.adc_min, lo, false);
+        if (lane == 0 && hi) fs_outside(outside, s.adc_hist, adc_min, adc_max, adc_max, hi, false);
+        if (lane == 0 && lo) fs_outside(outside, s.adc_hist, adc_min, adc_max, adc_min, lo, false);
     }
     barrier();
 
     // flush: CTA histogram (+ its power sums), per-bin sums
     double m[4] = {outside.m[0], outside.m[1], outside.m[2], outside.m[3]};
-    const int n_hist = p.adc_max - p.adc_min + 1;
+    const int n_hist = adc_max - adc_min + 1;
     for (int i = tid; i < FS_HIST; i += NT) {
         const unsigned int c = hist_s[i];
-        const int gidx = i + s.hist_lo - p.adc_min;
+        const int gidx = i + s.hist_lo - adc_min;
         if (c && gidx >= 0 && gidx < n_hist) {
             atomicAdd(s.adc_hist + gidx, (unsigned long long)c);
             const double x = (double)(i + s.hist_lo), cd = (double)c;

@@ -447,7 +447,7 @@ k_generate_scatter(const GenArgs a) {
     }
     __syncthreads();
     if (a.st.adc_hist)
-        cta_fused_stats<NT, 1>(a.st, p, trace0, a.n_traces, rows,
+        cta_fused_stats<NT, 1>(a.st, p.B, p.P, p.adc_min, p.adc_max, p.baseline, trace0, a.n_traces, rows,
                                smem_raw + stats_offset(gen_smem_bytes(B, n_tab, NT)));
     store_run<NT>(a, trace0, rows);
 }

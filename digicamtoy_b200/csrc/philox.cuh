@@ -111,8 +111,14 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_rk(u32x4 c, const RoundKeys
     return c;
 }
 
+#ifndef DCT_USE_ROUND_KEYS
+#define DCT_USE_ROUND_KEYS 1     // 0: key schedule computed per block (the round-1 form), for comparison
+#endif
 __host__ __device__ __forceinline__ u32x4 draw_block_rk(const RoundKeys& rk, const StreamKey& s, uint32_t stream,
                                                         uint32_t block) {
+#if !DCT_USE_ROUND_KEYS
+    return draw_block(s, stream, block);
+#endif
     u32x4 c;
     c.x = block;
     c.y = (stream << 24) | (s.ev_hi & 0x00FFFFFFu);

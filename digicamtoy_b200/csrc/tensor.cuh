@@ -63,10 +63,10 @@ constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
 #define DCT_TC_UNROLL 4                        // (the producer loop now works in groups of four pe: one NsbGroup per look at the ring state)
 #endif
 // mean pe per trace from which AUTO prefers this kernel over the sweep kernel: measured crossover
-// at ~60 pe / trace (0.25 GHz on the 240 ns window; profiles/r02/crossover_tensor.txt) -- below it the
+// at 55-60 pe / trace (0.25 GHz on the 240 ns window: 11.3 against 11.6 ms per 8192 events; profiles/r02/crossover_tensor.txt) -- below it the
 // per-cell hand-over (59 cells whatever the rate) costs more than the taps it saves.
 #ifndef DCT_TC_MIN_MEAN_PE
-#define DCT_TC_MIN_MEAN_PE 70.0
+#define DCT_TC_MIN_MEAN_PE 60.0
 #endif
 
 struct TensorArgs {
@@ -474,7 +474,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (a.st.adc_hist)
-            cta_fused_stats<TC_TRACES, 1>(a.st, p, trace0, a.n_traces, rows,
+            cta_fused_stats<TC_TRACES, 1>(a.st, p.B, p.P, p.adc_min, p.adc_max, p.baseline, trace0, a.n_traces, rows,
                                           smem_raw + stats_offset(tensor_smem_bytes(B, RING)));
         store_run<TC_TRACES>(a, trace0, rows);
     }

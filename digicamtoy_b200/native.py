@@ -137,9 +137,12 @@ class Handle:
         self.kernel = KERNEL_NAMES.get(self.lib.dct_selected_kernel(self.ptr), '?')
 
     def close(self):
-        if getattr(self, 'ptr', None) is not None and self.ptr.value:
-            self.lib.dct_destroy(self.ptr)
-            self.ptr = ctypes.c_void_p()
+        # forget the pointer BEFORE destroying it: during interpreter shutdown anything after the C
+        # call may raise (module globals are already gone), and a second close() -- the generator's
+        # __del__ and then this object's -- must not destroy the handle again
+        ptr, self.ptr = getattr(self, 'ptr', None), None
+        if ptr is not None and ptr.value:
+            self.lib.dct_destroy(ptr)
 
     def __del__(self):
         try:

@@ -139,8 +139,11 @@ def produce_level(config, filename, n_events, seed, device, finish=None):
     true_baseline, gen_seed = generator.true_baseline, generator.seed
     # replaces the loop :119-126; a level larger than one slab goes through one reused pinned slab
     slab_events = max(1, min(int(n_events), SLAB_BYTES // max(1, p.n_pixels * p.n_bins * 2)))
+    pinned = ()
     if slab_events >= n_events:
-        adc_count, cherenkov_time, cherenkov_photon = generator.generate_host(n_events, first_event=0)
+        from digicamtoy_b200.tracegenerator import PINNED
+        adc_count, cherenkov_time, cherenkov_photon = generator.generate_host(n_events, first_event=0, pool=PINNED)
+        pinned = generator.last_host_tensors              # back to the pool once the file is written
     else:
         adc_count = np.empty((n_events, p.n_pixels, p.n_bins), dtype=np.uint16 if generator.saturate[0] >= 0 else np.int16)
         cherenkov_time = np.empty((n_events, p.n_pixels, p.n_pulses), dtype=np.float32)
@@ -165,6 +168,9 @@ def produce_level(config, filename, n_events, seed, device, finish=None):
         writer.put('data/charge', cherenkov_photon.astype(np.float64), compress=True)
         writer.put('config/date', str(datetime.datetime.now()))
         path = writer.close()
+        if pinned:
+            from digicamtoy_b200.tracegenerator import PINNED
+            PINNED.release(*pinned)
         log.info('\t\t-|> File saved! Size = {}'.format(natural_size(os.path.getsize(path))))
         return path
 

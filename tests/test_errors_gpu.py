@@ -71,3 +71,31 @@ def test_many_handles_and_streams():
         torch.cuda.synchronize()
         assert torch.equal(o, again)
     assert outs[0].float().mean() < outs[3].float().mean()     # more NSB, higher pedestal
+
+
+def test_process_exits_cleanly_without_an_explicit_close():
+    """A generator that is never closed is destroyed once at interpreter shutdown -- by its own
+    __del__ or by its handle's, whichever runs first, never by both (round 2 found a double
+    dct_destroy there: glibc reported 'double free or corruption' at exit)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for kernel in ('sweep', 'tensor'):
+        out = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'exit_check.py'), kernel, 'noclose', '2'],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-1000:]
+        assert 'done ' + kernel in out.stdout
+        assert 'double free' not in out.stderr and 'corruption' not in out.stderr, out.stderr[-1000:]
+
+
+def test_calls_after_close_raise_instead_of_touching_freed_memory():
+    import torch
+    from digicamtoy_b200 import NTraceGenerator
+    g = NTraceGenerator(n_pixels=8, nsb_rate=0.1, seed=1)
+    g.generate(2)
+    torch.cuda.synchronize()
+    g.close()
+    g.close()                                   # idempotent
+    with pytest.raises(ValueError):
+        g.generate(2)

@@ -25,8 +25,8 @@ def on_grid_moments(cfg, kw):
     return cfg.baseline[:, None] + g * lam * m1 * s1h, g ** 2 * lam * m2 * s2h + cfg.sigma_e[:, None] ** 2 + 1 / 12
 
 
-def check(name, kw, n_events, chunk=16384):
-    g = NTraceGenerator(seed=12345, saturate=(-2000, 6000), **kw)
+def check(name, kw, n_events, chunk=16384, kernel='auto'):
+    g = NTraceGenerator(seed=12345, saturate=(-2000, 6000), kernel=kernel, **kw)
     st = CubeStats(g)
     buf = torch.empty((chunk, g.params.n_pixels, g.params.n_bins), dtype=torch.int16, device='cuda')
     done = 0
@@ -49,7 +49,9 @@ def check(name, kw, n_events, chunk=16384):
     print('   var : max rel dev %.2e (rounding term 1/12 included in the closed form)' % np.abs(v_hat / var_b - 1).max())
     return z
 
-check('ac_dc NSB 1 GHz, no pulse', workloads.c2_ac_dc(1.0, 0.), 200000)
+check('ac_dc NSB 1 GHz, no pulse', workloads.c2_ac_dc(1.0, 0.), 200000)                       # auto: tensor kernel
+check('ac_dc NSB 1 GHz, no pulse', workloads.c2_ac_dc(1.0, 0.), 200000, kernel='sweep')
+check('ac_dc NSB 0.66 GHz, no pulse', workloads.c2_ac_dc(0.66, 0.), 200000)                    # auto: tensor kernel
 check('ac_dc NSB 0.04 GHz, no pulse', workloads.c2_ac_dc(0.04, 0.), 200000)
 check('dark.yml, no pulse', workloads.c1_dark(0.), 100000)
 check('ac_dc NSB 1 GHz on the sampling grid (sub_binning=1), no pulse', dict(sub_binning=1, **workloads.c2_ac_dc(1.0, 0.)), 200000)
