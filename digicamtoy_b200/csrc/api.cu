@@ -83,6 +83,7 @@ struct dct_handle {
     float tc_v_scale = 0.0f;
     int tc_check_span = 1;
     float tc_y0 = 0.0f, tc_y_end = 0.0f;
+    double tc_err_lsb = 0.0;           // estimated rms of K1t's fp16 rounding in the analog sums [LSB]
     // host-output pipeline (dct_generate_host), created lazily
     cudaStream_t s_gen = nullptr, s_copy = nullptr;
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -435,9 +436,21 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                     "tensor kernel needs the polyphase table with %d taps, continuous NSB and an even number of <= %d bins",
                     dct::TC_TAPS, dct::TC_MAX_BINS);
     }
+    // K1t sums through fp16 moments: measured 2.6e-3 LSB rms on C4 (gain 2.5 LSB/pe, template peak 1,
+    // 1 GHz = 88 overlapping pe), i.e. 1.1e-4 x gain x template peak x sqrt(overlapping pe).  AUTO only
+    // takes it while that estimate stays below 0.01 LSB (the reference normalises the template by its
+    // maximum INSIDE the simulated window, :144-149, so short or late windows can scale it up a lot).
+    double tc_err_lsb = 0.0;
+    {
+        double h_max = 0.0, g_max = 0.0, r_max = 0.0;
+        for (int m = 0; m < n_iv; ++m) h_max = std::max(h_max, std::fabs(c->coef[4 * m]));
+        for (int i = 0; i < P; ++i) { g_max = std::max(g_max, std::fabs(c->gain[i])); r_max = std::max(r_max, c->nsb_rate[i]); }
+        tc_err_lsb = 1.1e-4 * g_max * h_max * std::sqrt(std::max(1.0, r_max * (x_hi - x_lo)));
+    }
+    h->tc_err_lsb = tc_err_lsb;
     if (want == DCT_KERNEL_AUTO)
         want = grid_ok ? DCT_KERNEL_GRID
-             : (tensor_ok && h->tc_n_cells > 0 && h->mean_pe_per_trace >= DCT_TC_MIN_MEAN_PE) ? DCT_KERNEL_TENSOR
+             : (tensor_ok && h->tc_n_cells > 0 && h->mean_pe_per_trace >= DCT_TC_MIN_MEAN_PE && tc_err_lsb <= 0.01) ? DCT_KERNEL_TENSOR
              : (sweep_ok && h->mean_pe_per_trace >= dct::SWEEP_MIN_MEAN_PE) ? DCT_KERNEL_SWEEP
                                                                             : DCT_KERNEL_SCATTER;
     h->kernel = want;

@@ -86,3 +86,54 @@ def test_tensor_kernel_handles_per_pixel_rates_dark_pixels_and_partial_blocks():
     from digicamtoy_b200 import workloads
     with pytest.raises(ValueError):
         gen(seed=1, kernel='tensor', **workloads.c1_dark(n_photon=1))
+
+
+@pytest.mark.parametrize('window', [dict(time_start=0, time_end=320), dict(time_start=0, time_end=16),
+                                    dict(time_start=-40, time_end=104), dict(time_start=0, time_end=8)])
+def test_tensor_kernel_window_shapes(window):
+    """The largest window the accumulator holds (80 bins), small ones (4 and 2 bins), one that does
+    not start at 0: same photo-electrons as the sweep kernel, so the analog sums agree to the fp16
+    rounding of the moments -- which scales with the template: the reference normalises it by its
+    maximum INSIDE the simulated window (:144-149), 1.8x larger than usual for the 8 ns window."""
+    import torch
+    kw = dict(ACDC)
+    kw.update(window)
+    kw.update(n_pixels=70, nsb_rate=0.9, n_photon=20., time_signal=kw['time_start'] + 20)
+    gs, gt = gen(seed=11, kernel='sweep', **kw), gen(seed=11, kernel='tensor', **kw)
+    (a, an_s), (b, an_t) = gs.generate_analog(60), gt.generate_analog(60)
+    torch.cuda.synchronize()
+    assert a.shape[2] == (kw['time_end'] - kw['time_start']) // 4
+    h_max = float(np.abs(gs.pulse_template(gs.params.knot_x)).max())
+    assert 0.99 < h_max < 2.0
+    rms = float(((an_t.double() - an_s.double()) * float(gs.gain[0])).pow(2).mean().sqrt())
+    assert rms < 3.2e-3 * h_max, (rms, h_max)
+    d = (a.int() - b.int()).cpu().numpy()
+    assert np.abs(d).max() <= 1 and (d != 0).mean() < 3.5e-3 * h_max
+    assert a.float().std() > 1.0
+
+
+def test_auto_leaves_the_tensor_kernel_alone_when_its_rounding_would_show():
+    """AUTO picks K1t only while the estimated fp16 rounding stays below 0.01 LSB: not for a gain of
+    60 LSB per pe, nor for a window that starts after the pulse maximum (template scaled up ~30x)."""
+    base = dict(n_pixels=8, nsb_rate=1.0, n_photon=0., **ACDC)
+    assert gen(seed=1, **base).kernel == 'tensor'
+    assert gen(seed=1, **{**base, 'gain': 60., 'gain_nsb': False}).kernel == 'sweep'
+    assert gen(seed=1, **{**base, 'time_start': 100, 'time_end': 300}).kernel == 'sweep'
+    assert gen(seed=1, kernel='tensor', **{**base, 'gain': 60., 'gain_nsb': False}).kernel == 'tensor'   # explicit choice stands
+
+
+def test_two_tensor_generators_on_two_streams_share_the_tensor_memory():
+    """Two K1t launches in flight at once: every SM's 512 TMEM columns are taken by whichever CTAs
+    arrive first, the others wait in tcgen05.alloc -- results must not depend on it."""
+    import torch
+    kw = dict(n_pixels=1296, nsb_rate=1.0, n_photon=5., **ACDC)
+    g1, g2 = gen(seed=1, kernel='tensor', **kw), gen(seed=2, kernel='tensor', **kw)
+    ref1, ref2 = g1.generate(300, first_event=0), g2.generate(300, first_event=0)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        o1 = g1.generate(300, first_event=0)
+    with torch.cuda.stream(s2):
+        o2 = g2.generate(300, first_event=0)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, ref1) and torch.equal(o2, ref2)
