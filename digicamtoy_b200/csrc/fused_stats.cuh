@@ -13,6 +13,10 @@
 #pragma once
 #include "device_params.cuh"
 
+#ifndef DCT_FUSED_STATS
+#define DCT_FUSED_STATS 1      // 0: compile the fused statistics out of the generation kernels (timing experiments)
+#endif
+
 namespace dct {
 
 constexpr int FS_WIN = 16;         // values per thread-private column set

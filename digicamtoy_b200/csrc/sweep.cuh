@@ -227,7 +227,7 @@ k_generate_sweep(const GenArgs a) {
         digitise_trace(p, a.rk, t, row);
     }
     __syncthreads();
-    if (a.st.adc_hist)
+    if (DCT_FUSED_STATS && a.st.adc_hist)
         cta_fused_stats<NT, 1>(a.st, p.B, p.P, p.adc_min, p.adc_max, p.baseline, trace0, a.n_traces, rows,
                                smem_raw + stats_offset(gen_smem_bytes(B, TAPS * PHASES, NT)));
     store_run<NT>(a, trace0, rows);

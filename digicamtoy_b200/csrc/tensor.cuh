@@ -473,7 +473,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             digitise_trace(p, a.rk, t, row);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (a.st.adc_hist)
+        if (DCT_FUSED_STATS && a.st.adc_hist)
             cta_fused_stats<TC_TRACES, 1>(a.st, p.B, p.P, p.adc_min, p.adc_max, p.baseline, trace0, a.n_traces, rows,
                                           smem_raw + stats_offset(tensor_smem_bytes(B, RING)));
         store_run<TC_TRACES>(a, trace0, rows);

@@ -14,7 +14,7 @@ import numpy as np
 
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = 'libdigicamtoy_sm100.so'
-LIB_PATH = os.path.join(PACKAGE_DIR, LIB_NAME)
+LIB_PATH = os.environ.get('DCT_LIB_PATH') or os.path.join(PACKAGE_DIR, LIB_NAME)    # (override: timing experiments against older builds)
 CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
 
 DCT_ABI_VERSION = 2
@@ -80,18 +80,20 @@ def load_library():
     lib.dct_selected_kernel.argtypes = [vp]
     lib.dct_generate.argtypes = [vp, u64, u64, u32, vp, vp, vp, vp]
     lib.dct_generate_host.argtypes = [vp, u64, u64, u32, vp, vp, vp]
-    lib.dct_generate_analog.argtypes = [vp, u64, u64, u32, vp, vp, vp]
+    if hasattr(lib, 'dct_generate_analog'):
+        lib.dct_generate_analog.argtypes = [vp, u64, u64, u32, vp, vp, vp]
     for f in (lib.dct_replay_f64, lib.dct_replay_f32):
         f.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.dct_generate_stats.argtypes = [vp, u64, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
+    if hasattr(lib, 'dct_generate_stats'):          # (absent only in older builds loaded through DCT_LIB_PATH)
+        lib.dct_generate_stats.argtypes = [vp, u64, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
     lib.dct_stats_accumulate.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp]
     lib.dct_write_calibrate.argtypes = [vp, ctypes.c_size_t, vp]
     lib.dct_trace_pe.argtypes = [vp, u64, u64, u32, u32, vp, vp, vp, vp, vp]
     lib.dct_test_sample.argtypes = [u32, ctypes.c_double, ctypes.c_double, u64, u32, vp, vp]
     for name in EXPORTED_SYMBOLS:
-        if name not in ('dct_last_error', 'dct_destroy'):
+        if name not in ('dct_last_error', 'dct_destroy') and hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
-    if lib.dct_abi_version() != DCT_ABI_VERSION:
+    if lib.dct_abi_version() != DCT_ABI_VERSION and not os.environ.get('DCT_LIB_PATH'):
         raise RuntimeError('{} has ABI version {}, expected {}'.format(
             LIB_PATH, lib.dct_abi_version(), DCT_ABI_VERSION))
     _lib = lib
