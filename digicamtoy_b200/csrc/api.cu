@@ -79,7 +79,7 @@ struct dct_handle {
     double mean_baseline = 0.0;
     // tensor-core kernel (K1t): coefficient tiles live in the arena
     const __half* tc_coef = nullptr;
-    int tc_n_cells = 0, tc_col_shift = 0;
+    int tc_n_cells = 0, tc_col_shift = 0, tc_col0 = 16, tc_n_cells32 = 0;
     float tc_v_scale = 0.0f;
     int tc_check_span = 1;
     float tc_y0 = 0.0f, tc_y_end = 0.0f;
@@ -306,7 +306,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     // four tiles: hi, lo, and both again one row further down (for cells that start on an odd column)
     const size_t tc_tile = (size_t)dct::TC_N * dct::TC_K;
     std::vector<uint16_t> tc_coef(4 * tc_tile, 0);
-    const bool tensor_ok = dct::tensor_supported(p);
+    bool tensor_ok = dct::tensor_supported(p);
     if (tensor_ok) {
         const double a1 = 0.5 * dx, a2 = a1 * a1, a3 = a2 * a1;
         for (int n = 0; n < dct::TC_TAPS; ++n)
@@ -333,7 +333,9 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         const int n_time = (int)std::ceil(((double)p.off0 + (c->t_end - c->t0)) / c->dt) + 1;
         const int n_useful = p.B - 1 + p.n_drop - p.cell0;
         h->tc_n_cells = std::max(0, std::min(n_time, n_useful));
-        h->tc_col_shift = p.cell0 + 1 - p.n_drop + dct::TC_COL0;
+        const dct::TensorLayout lay = dct::tensor_layout(p.B, p.n_drop, p.cell0, h->tc_n_cells);
+        tensor_ok = lay.ok;
+        h->tc_col_shift = lay.col_shift; h->tc_col0 = lay.col0; h->tc_n_cells32 = lay.n_cells32;
         h->tc_v_scale = (float)(2.0 / dx);
         // the cell test ends the pe stream by itself when the useful cells end a cell before the window
         h->tc_check_span = ((double)n_useful + 1.0) * c->dt <= (double)p.off0 + (c->t_end - c->t0) ? 0 : 1;
@@ -496,6 +498,7 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
         ta.g = a;
         ta.coef = h->tc_coef;
         ta.n_cells = h->tc_n_cells; ta.col_shift = h->tc_col_shift; ta.v_scale = h->tc_v_scale;
+        ta.col0 = h->tc_col0; ta.n_cells32 = h->tc_n_cells32;
         ta.check_span = h->tc_check_span;
         ta.y0 = h->tc_y0; ta.y_end = h->tc_y_end;
         return dct::launch_tensor(h->device, ta, st, g_err, sizeof(g_err));

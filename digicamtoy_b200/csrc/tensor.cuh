@@ -44,9 +44,37 @@ constexpr int TC_PHASES = 8;
 constexpr int TC_K = TC_PHASES * 4;            // fp16 K per cell: 8 phases x 4 moments
 constexpr int TC_SLOT_BYTES = TC_TRACES * TC_K * 2;      // 8 KiB
 constexpr int TC_G_BYTES = TC_N * TC_K * 2;              // 2 KiB per coefficient tile
-constexpr int TC_COL0 = 16;                    // TMEM column of kept bin 0
 constexpr int TC_TMEM_COLS = 128;
-constexpr int TC_MAX_BINS = TC_TMEM_COLS - TC_COL0 - TC_N;   // 80
+constexpr int TC_MAX_BINS = 100;
+// Accumulator column of kept bin 0.  A cell's MMA writes TC_N (32) columns from its own column on, so
+// windows of up to 80 bins keep 16 spare columns in front and 32 behind the kept bins.  Longer ones
+// (dark.yml: 92 bins) start at column 10 and let the last few cells -- whose taps 16.. land beyond the
+// window anyway -- run with N = 16 so that nothing is written past column 127 (tensor_layout).
+__host__ __device__ inline int tensor_col0(int B) { return B <= 80 ? 16 : 10; }
+
+struct TensorLayout {
+    int col0, col_shift;        // column of kept bin 0; column of tap 0 of cell c (relative to cell0) = c + col_shift
+    int n_cells32;              // cells 0 .. n_cells32-1 use N = 32, the rest N = 16
+    bool ok;
+};
+
+// Column plan for `n_cells` cells; ok = every tap that lands on a kept bin is covered.
+inline TensorLayout tensor_layout(int B, int n_drop, int cell0, int n_cells) {
+    TensorLayout L;
+    L.col0 = tensor_col0(B);
+    L.col_shift = cell0 + 1 - n_drop + L.col0;
+    L.n_cells32 = n_cells;
+    L.ok = L.col_shift >= 0;
+    const int last_col = L.col0 + B - 1;                       // column of the last kept bin
+    for (int c = 0; c < n_cells; ++c) {
+        const int col = c + L.col_shift, d = col & ~1;         // odd columns accumulate from the even one below
+        if (d + TC_N <= TC_TMEM_COLS) continue;                // N = 32 fits
+        if (c < L.n_cells32) L.n_cells32 = c;
+        const int taps_needed = last_col - col + 1;            // taps 0 .. taps_needed-1 land on kept bins
+        if (d + 16 > TC_TMEM_COLS || (col - d) + taps_needed > 16) L.ok = false;
+    }
+    return L;
+}
 #ifndef DCT_TC_RING
 #define DCT_TC_RING 5                          // 40 KiB of moment slots: four CTAs (all 512 TMEM columns) per SM
 #endif
@@ -78,6 +106,8 @@ struct TensorArgs {
     const __half* coef;
     int n_cells;                 // cells cell0 .. cell0 + n_cells - 1 can reach a kept bin
     int col_shift;               // accumulator column of tap 0 of cell c (relative to cell0): c + col_shift
+    int col0;                    // accumulator column of kept bin 0
+    int n_cells32;               // cells below it issue N = 32 MMAs, the others N = 16 (end of a long window)
     float v_scale;               // 2 / knot_dx
     int check_span;              // 0: the cell test alone ends the pe stream (see k_generate_tensor)
     float y0, y_end;             // producer clock in knot steps from the start of cell0: first value, end of the stream
@@ -92,7 +122,7 @@ __host__ __device__ inline int tc_tile_offset(int row, int k) {
 
 inline bool tensor_supported(const DevParams& p) {
     return p.n_phase == TC_PHASES && p.n_taps == TC_TAPS && p.sub_binning <= 0 && p.B <= TC_MAX_BINS &&
-           p.cell0 >= 0 && p.n_drop - 1 - p.cell0 <= TC_COL0 && (p.B & 1) == 0;
+           p.cell0 >= 0 && p.n_drop - 1 - p.cell0 <= tensor_col0(p.B) && (p.B & 1) == 0;
 }
 
 __host__ __device__ inline size_t tensor_smem_bytes(int B, int ring) {
@@ -116,14 +146,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return lo | (hi << 32);
 }
 
-// instruction descriptor: D = F32, A = B = F16, both K-major, N = 32, M = 128
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_TRACES >> 4) << 24);
+// instruction descriptor: D = F32, A = B = F16, both K-major, N = 32 (or 16), M = 128
+__host__ __device__ constexpr uint32_t idesc_n(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TRACES >> 4) << 24); }
 
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate,
+                                        uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -291,10 +322,11 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
                     const uint32_t d = tmem + (col & ~1u);
                     const uint32_t g = g_addr + (col & 1u) * (2 * TC_G_BYTES);      // odd column: shifted tiles
                     const uint64_t a0 = tc::smem_desc(slot), a1 = tc::smem_desc(slot + 256);
-                    tc::mma_f16(d, a0, tc::smem_desc(g), 1u);
-                    tc::mma_f16(d, a1, tc::smem_desc(g + 256), 1u);
-                    tc::mma_f16(d, a0, tc::smem_desc(g + TC_G_BYTES), 1u);
-                    tc::mma_f16(d, a1, tc::smem_desc(g + TC_G_BYTES + 256), 1u);
+                    const uint32_t idesc = c < ta.n_cells32 ? tc::idesc_n(TC_N) : tc::idesc_n(16);
+                    tc::mma_f16(d, a0, tc::smem_desc(g), 1u, idesc);
+                    tc::mma_f16(d, a1, tc::smem_desc(g + 256), 1u, idesc);
+                    tc::mma_f16(d, a0, tc::smem_desc(g + TC_G_BYTES), 1u, idesc);
+                    tc::mma_f16(d, a1, tc::smem_desc(g + TC_G_BYTES + 256), 1u, idesc);
                     tc::mma_commit(done + 8u * (uint32_t)slot_i);
                 }
                 __syncwarp();
@@ -457,8 +489,8 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             const TraceId t = trace_id(a, trace0 + tid);
             add_signal_pulses(a, t, p.coef32, row, p.xt[t.pixel], p.sigma1[t.pixel]);
         }
-        // NSB sums: accumulator columns TC_COL0 .. TC_COL0 + B - 1 of this thread's TMEM lane
-        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + TC_COL0;
+        // NSB sums: accumulator columns col0 .. col0 + B - 1 of this thread's TMEM lane
+        const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)ta.col0;
         for (int b0 = 0; b0 < B; b0 += 16) {
             float d[16];
             tc::tmem_ld16(tw + b0, d);

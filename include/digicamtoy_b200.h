@@ -52,7 +52,7 @@ enum {
     DCT_KERNEL_SWEEP = 2,    /* time-ordered register window (default template at 4 ns sampling) */
     DCT_KERNEL_GRID = 3,     /* sub_binning > 0 only: fixed on-grid taps, register window          */
     DCT_KERNEL_TENSOR = 4    /* high NSB rates: per-cell pe moments x coefficient tile on tcgen05.mma
-                                (default template at 4 ns sampling, even n_bins <= 80)              */
+                                (default template at 4 ns sampling, even n_bins <= 100)              */
 };
 
 /* Everything NTraceGenerator.__init__ derives (reference :52-157), already transformed on the

@@ -73,7 +73,7 @@ def test_tensor_kernel_moments_against_closed_form(rate):
 
 def test_tensor_kernel_handles_per_pixel_rates_dark_pixels_and_partial_blocks():
     """Pixels without NSB, rates from 1 MHz to 2 GHz in one camera, a trace count that is not a
-    multiple of the 128-trace CTA, the 92-bin window falls back (more bins than accumulator columns)."""
+    multiple of the 128-trace CTA; windows the accumulator cannot hold are refused."""
     import torch
     rates = np.concatenate([np.zeros(3), np.logspace(-3, 0.3, 58)])
     kw = dict(n_pixels=61, nsb_rate=rates, n_photon=3., **ACDC)
@@ -83,9 +83,36 @@ def test_tensor_kernel_handles_per_pixel_rates_dark_pixels_and_partial_blocks():
     d = (a.int() - b.int()).cpu().numpy()
     assert np.abs(d).max() <= 1 and (d != 0).mean() < 5e-3
     assert np.array_equal(a[:, :3].cpu().numpy(), b[:, :3].cpu().numpy())      # no NSB: nothing goes through fp16
-    from digicamtoy_b200 import workloads
-    with pytest.raises(ValueError):
-        gen(seed=1, kernel='tensor', **workloads.c1_dark(n_photon=1))
+    with pytest.raises(ValueError):                          # more bins than the accumulator has columns for
+        gen(seed=1, kernel='tensor', n_pixels=4, nsb_rate=1.0, **{**ACDC, 'time_end': 408})
+    with pytest.raises(ValueError):                          # odd number of bins
+        gen(seed=1, kernel='tensor', n_pixels=4, nsb_rate=1.0, **{**ACDC, 'time_end': 204})
+
+
+@pytest.mark.parametrize('time_end', [368, 400])
+def test_tensor_kernel_on_dark_yaml_length_windows(time_end):
+    """92 bins (dark.yml, the commissioning grid of config_files/generate.py) and 100 bins: the kept
+    bins start at accumulator column 10 and the last cells issue N = 16 MMAs so that nothing is
+    written past column 127; every kept bin still gets all its taps."""
+    import torch
+    kw = dict(n_pixels=140, nsb_rate=1.2, n_photon=30., **{**ACDC, 'time_end': time_end, 'time_signal': 300.})
+    gs, gt = gen(seed=4, kernel='sweep', **kw), gen(seed=4, kernel='tensor', **kw)
+    assert gen(seed=4, **kw).kernel == 'tensor'              # AUTO takes it too
+    (a, an_s), (b, an_t) = gs.generate_analog(40), gt.generate_analog(40)
+    torch.cuda.synchronize()
+    assert a.shape[2] == time_end // 4
+    d = ((an_t.double() - an_s.double()) * float(gs.gain[0])).cpu().numpy()
+    rms_per_bin = np.sqrt((d ** 2).mean(axis=(0, 1)))
+    assert rms_per_bin.max() < 4e-3, rms_per_bin             # no bin misses a tap (that would be O(1) LSB)
+    dd = (a.int() - b.int()).cpu().numpy()
+    assert np.abs(dd).max() <= 1 and (dd != 0).mean() < 5e-3
+    kwq = dict(kw, n_photon=0.)
+    c = gen(seed=9, kernel='tensor', saturate=None, **kwq).generate(1500)
+    torch.cuda.synchronize()
+    c = c.cpu().numpy().astype(np.float64)
+    mean, var = orc.closed_form_moments(orc.make_config(**kwq))
+    z = (c.mean(axis=0) - mean) / np.sqrt(var / c.shape[0])
+    assert np.abs(z).max() < 6
 
 
 @pytest.mark.parametrize('window', [dict(time_start=0, time_end=320), dict(time_start=0, time_end=16),
