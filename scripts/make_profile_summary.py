@@ -7,14 +7,18 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(root, 'profiles', rnd)
 os.makedirs(out_dir, exist_ok=True)
 rows = []
-for path in sorted(glob.glob(os.path.join(root, 'gpurun_out', 'bench_*.json'))):
+# bench lines already curated into profiles/<round>/ win; anything else comes from gpurun_out/
+paths = {os.path.basename(p_): p_ for p_ in glob.glob(os.path.join(root, 'gpurun_out', 'bench_*.json'))}
+paths.update({os.path.basename(p_): p_ for p_ in glob.glob(os.path.join(out_dir, 'bench_*.json'))})
+for name_, path in sorted(paths.items()):
     try:
         line = [l for l in open(path).read().strip().splitlines() if l.startswith('{')][-1]
         j = json.loads(line)
     except Exception:
         continue
-    shutil.copy(path, os.path.join(out_dir, os.path.basename(path)))
-    rows.append((os.path.basename(path), j))
+    if os.path.dirname(path) != out_dir:
+        shutil.copy(path, os.path.join(out_dir, name_))
+    rows.append((name_, j))
 peaks = json.load(open(os.path.join(root, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(root, 'MEASURED_PEAKS.json')) else {}
 with open(os.path.join(out_dir, 'SUMMARY.md'), 'w') as f:
     f.write('# Measured on B200 (%s)\n\n' % rnd)
@@ -28,7 +32,7 @@ with open(os.path.join(out_dir, 'SUMMARY.md'), 'w') as f:
         k = j.get('clocks') or {}
         cfg = j.get('config', {})
         f.write('| %s | %s | %s | %s | %s | %.3e | %s | %.2f | %s | %s | %s | %s | %s | %s | %s |\n' % (
-            name, j.get('impl', 'b200'), cfg.get('workload', '')[:40], cfg.get('kernel', '-'), j.get('n_gpus'),
+            name, j.get('impl', 'b200'), cfg.get('workload', '')[:40], (j.get('run_details') or cfg).get('kernel', '-'), j.get('n_gpus'),
             j['value'], ('%.3e' % j['events_per_s']) if 'events_per_s' in j else '-', j['ms_per_step'],
             ('%.2f' % r['kernel_ms']) if r else '-', ('%.1f' % r['achieved']) if r else '-',
             ('%.4f' % r['frac']) if r else '-', ('%.3e' % e['value']) if e else '-',
@@ -51,8 +55,12 @@ if os.path.exists(lp):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, 'SUMMARY.md'), 'a') as f:
         f.write('\n## ncu launch list of `python bench.py --no-cpu-baseline` (first 200 launches, `launches_bench_default.csv`)\n\n')
-        f.write('Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.  In the\n'
-                'CUDA-event timing of the same command K1 is 59.8 of 62.2 ms per step (96 %).\n\n')
+        ev = next((j for n_, j in rows if n_ == 'bench_n1.json'), None)
+        f.write('Per-launch times under ncu are cold-cache and serialised: compare shares, not absolutes.\n')
+        if ev:
+            f.write('In the CUDA-event timing of the same command K1 is %.1f of %.1f ms per step (%.0f %%).\n' % (
+                ev['roofline']['kernel_ms'], ev['ms_per_step'], 100 * ev['roofline']['kernel_ms'] / ev['ms_per_step']))
+        f.write('(Launches shorter than a full step are the 64 MiB chunks of the end-to-end leg and the iterator batches.)\n\n')
         f.write('| kernel | launches | total ms | share |\n|---|---|---|---|\n')
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %d | %.2f | %.1f %% |\n' % (k, v[0], v[1], 100 * v[1] / tot))
