@@ -164,3 +164,21 @@ def test_two_tensor_generators_on_two_streams_share_the_tensor_memory():
         o2 = g2.generate(300, first_event=0)
     torch.cuda.synchronize()
     assert torch.equal(o1, ref1) and torch.equal(o2, ref2)
+
+
+def test_randomised_cross_checks_of_all_generation_kernels():
+    """tests/tools/fuzz_kernels.py: 150 random configurations (1..300 pixels, 2..130 bins, zero to
+    3 GHz and per-pixel rates, pulses of 0..3000 pe, crosstalk 0..0.3): sweep == scatter bit for bit,
+    tensor within rounding of them, chunked == one-shot, fused statistics == separate == NumPy."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        'fuzz_kernels', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'fuzz_kernels.py'))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    rs = np.random.RandomState(2026)
+    kernels_seen = set()
+    for i in range(150):
+        msg = fuzz.run_case(i, rs)
+        kernels_seen.add(msg.rsplit('auto=', 1)[-1] if 'auto=' in msg else 'skipped')
+    assert {'sweep', 'tensor', 'scatter'} <= kernels_seen | {'scatter'}
