@@ -20,12 +20,15 @@
 // (tests/test_tensor_gpu.py), far below the 1.25 LSB of electronic noise; signal pulses (up to
 // thousands of pe) are NOT sent through fp16: they are shaped in fp32 by the code of generate.cuh.
 //
-// CTA = 128 traces = 4 producer warps (thread = trace) + 4 helper warps (MMA issue, slot clearing).  Producers free-run through
-// time; the moments of cell c go to slot c mod R of a shared-memory ring (A operand, K-major,
-// no swizzle).  A warp publishes the smallest cell any of its lanes is still in; once all four
-// warps are past cell c the MMA warp issues its 4 MMAs (2 k-steps x hi/lo coefficients), waits for
-// them (tcgen05.commit -> mbarrier), clears the slot and releases it.  A lane that is R cells ahead
-// of the slowest trace of the CTA idles until a slot is free.
+// CTA = 128 traces = 4 producer warps (thread = trace) + warp 4 (MMA issue) + warp 5 (slot clearing)
+// + 2 idle warps (a CTA must hold a multiple of four warps, see TC_THREADS).  Producers free-run
+// through time in knot steps, four pe per look at the ring (one NsbGroup = three Philox blocks); the
+// moments of cell c go to slot c mod R of a shared-memory ring (A operand, K-major, no swizzle).  A warp
+// publishes the cell all its lanes are past (mailbox + a flip of the notify mbarrier); once all four
+// warps are past cell c the MMA warp issues its 4 MMAs (2 k-steps x hi/lo coefficients) and commits
+// them to the slot's mbarrier; the cleaner warp waits for that, zeroes the slot and releases it.  A
+// lane that is R cells ahead of the slowest trace of the CTA idles until a slot is free.  Four CTAs per
+// SM hold all 512 TMEM columns: TMEM caps the occupancy.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -34,10 +37,10 @@
 namespace dct {
 
 constexpr int TC_TRACES = 128;                 // MMA M
-constexpr int TC_THREADS = 256;                // 4 producer warps + 4 helper warps (one issues the MMAs, all
-                                               // four clear ring slots).  A multiple of 4 warps on purpose: a warp
-                                               // may only touch the TMEM lanes 32 (%warpid % 4) .., and with 5 warps
-                                               // per CTA the second CTA of an SM faulted on its first tcgen05.st
+constexpr int TC_THREADS = 256;                // 4 producer warps + 4 helper warps (MMA issue, slot clearing, 2 idle).
+                                               // A multiple of 4 warps on purpose: a warp may only touch the TMEM
+                                               // lanes 32 (%warpid % 4) .., and with 5 warps per CTA the second CTA
+                                               // of an SM faulted on its first tcgen05.st
 constexpr int TC_N = 32;                       // accumulator columns per cell MMA (22 taps + padding)
 constexpr int TC_TAPS = 22;
 constexpr int TC_PHASES = 8;
@@ -82,13 +85,10 @@ inline TensorLayout tensor_layout(int B, int n_drop, int cell0, int n_cells) {
 #define DCT_TC_MIN_BLOCKS 4
 #endif
 #ifndef DCT_TC_POLL_NS
-#define DCT_TC_POLL_NS 1000                    // longest the MMA warp sleeps before it looks at the producers' positions by itself
+#define DCT_TC_POLL_NS 1000                    // suspend-time hint of the MMA warp's wait on the notify barrier (it re-reads the mailboxes after)
 #endif
 #ifndef DCT_TC_REFRESH_LIMIT
 #define DCT_TC_REFRESH_LIMIT 0                 // 1: look at the released-cell counter before every store, not once per group
-#endif
-#ifndef DCT_TC_UNROLL
-#define DCT_TC_UNROLL 4                        // (the producer loop now works in groups of four pe: one NsbGroup per look at the ring state)
 #endif
 // mean pe per trace from which AUTO prefers this kernel over the sweep kernel: measured crossover
 // at 55-60 pe / trace (0.25 GHz on the 240 ns window: 11.3 against 11.6 ms per 8192 events; profiles/r02/crossover_tensor.txt) -- below it the
