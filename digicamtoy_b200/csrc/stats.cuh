@@ -129,7 +129,11 @@ k_stats(const StatsArgs a) {
 constexpr int STATS_WIN = DCT_STATS_WIN;
 constexpr int STATS_ROWS = 128;               // traces per tile = threads per CTA
 constexpr int STATS_CHARGE_WIN = 1024;        // CTA-private window of the charge histogram
-constexpr int STATS_PRIV_COLS = (STATS_ROWS / 32) * STATS_WIN;                 // (warp, value) columns
+#ifndef DCT_STATS_SETS
+#define DCT_STATS_SETS 1      // 2: separate column sets for the low and the high half-word of a cube word (two independent
+#endif                        //    read-modify-write chains per thread)
+constexpr int STATS_SETS = DCT_STATS_SETS;
+constexpr int STATS_PRIV_COLS = (STATS_ROWS / 32) * STATS_WIN * STATS_SETS;    // (set, warp, value) columns
 constexpr int STATS_PRIV_WORDS = STATS_PRIV_COLS * 16;                         // 32-bit words of the columns
 // (two independent column sets -- one per half-word -- were measured: the shorter dependency chain
 //  did not pay for the occupancy lost to the extra 16 KB: 3.2 ms instead of 2.4 ms per C4 cube)
@@ -179,6 +183,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
     unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;      // my column: priv[w * 32]
+    unsigned short* priv_hi = priv + (STATS_SETS - 1) * (STATS_ROWS / 32) * STATS_WIN * 32;   // second set (or the same)
     for (int i = tid; i < n_hist_s + STATS_CHARGE_WIN + STATS_PRIV_WORDS; i += STATS_ROWS)
         hist_s[i] = 0u;
     __syncthreads();
@@ -250,7 +255,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
                 if (a.adc_hist && mine) {
                     const unsigned h0 = (unsigned)(v0 - win_lo), h1 = (unsigned)(v1 - win_lo);
                     if (h0 < (unsigned)STATS_WIN) priv[h0 * 32] += 1; else hist_rare(v0);
-                    if (h1 < (unsigned)STATS_WIN) priv[h1 * 32] += 1; else hist_rare(v1);
+                    if (h1 < (unsigned)STATS_WIN) priv_hi[h1 * 32] += 1; else hist_rare(v1);
                 }
             }
             if (beyond) {                                        // compact layout, bright traces only
@@ -308,8 +313,10 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
             if (a.adc_hist && my_samples >= 60000) {             // 16-bit columns: fold this warp's window
                 __syncwarp();
                 for (int w = 0; w < STATS_WIN; ++w) {
-                    const unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)priv[w * 32]);
+                    unsigned int mine_c = priv[w * 32];
                     priv[w * 32] = 0;
+                    if (STATS_SETS > 1) { mine_c += priv_hi[w * 32]; priv_hi[w * 32] = 0; }
+                    const unsigned int c = __reduce_add_sync(0xffffffffu, mine_c);
                     if (lane == 0 && c) hist_add(win_lo + w, c);
                 }
                 my_samples = 0;

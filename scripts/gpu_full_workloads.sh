@@ -4,7 +4,7 @@ python bench.py --steps 61 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/be
 tail -n 1 gpurun_out/bench_c4_full_1e6.json | python -c "
 import sys, json
 j = json.loads(sys.stdin.read())
-n = j['steps'] * j['config']['events_per_step_per_gpu']
+n = j['steps'] * j['run_details']['events_per_step_per_gpu']
 print('C4 full: %d events in %.2f s (%.3e events/s, %.3e samples/s), K1 %.2f ms/step' % (n, j['steps'] * j['ms_per_step'] / 1e3, j['events_per_s'], j['value'], j['roofline']['kernel_ms']))
 "
 python tests/tools/acdc_levels.py | tee gpurun_out/levels_table.md
