@@ -87,6 +87,9 @@ inline TensorLayout tensor_layout(int B, int n_drop, int cell0, int n_cells) {
 #ifndef DCT_TC_POLL_NS
 #define DCT_TC_POLL_NS 1000                    // suspend-time hint of the MMA warp's wait on the notify barrier (it re-reads the mailboxes after)
 #endif
+#ifndef DCT_TC_GROUPS
+#define DCT_TC_GROUPS 1                        // NsbGroups (four pe each) a lane draws per look at the ring state
+#endif
 #ifndef DCT_TC_REFRESH_LIMIT
 #define DCT_TC_REFRESH_LIMIT 0                 // 1: look at the released-cell counter before every store, not once per group
 #endif
@@ -368,14 +371,17 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         auto nsb_block = [&](uint32_t block) { return draw_block_rk(a.rk, t.key, STREAM_NSB, block); };
         const uint32_t n8 = (uint32_t)n_cells * TC_PHASES;
 
-        // Lane state: a queue of the four pe of one NsbGroup (knot interval gq = 8 cell + j, amplitude,
-        // offset), nq = the next one to store (4: queue empty, draw the next group).  A pe past the end
+        // Lane state: a queue of the pe of one (or two) NsbGroups (knot interval gq = 8 cell + j, amplitude,
+        // offset), nq = the next one to store (NQ: queue empty, draw the next group).  A pe past the end
         // of the stream carries gq >= n8 and is never stored (the write limit never exceeds n8), so a
         // finished lane simply keeps its queue.
         float y = ta.y0;
-        uint32_t gq0 = n8, gq1 = n8, gq2 = n8, gq3 = n8;
-        float Aq0 = 0.f, Aq1 = 0.f, Aq2 = 0.f, Aq3 = 0.f, vq0 = 0.f, vq1 = 0.f, vq2 = 0.f, vq3 = 0.f;
-        int nq = (rate > 0.0f) ? 4 : 0;
+        constexpr int NQ = 4 * DCT_TC_GROUPS;            // pe per look at the ring: one or two NsbGroups
+        uint32_t gq[NQ];
+        float Aq[NQ], vq[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) { gq[k] = n8; Aq[k] = 0.f; vq[k] = 0.f; }
+        int nq = (rate > 0.0f) ? NQ : 0;
         uint32_t cur8 = (rate > 0.0f) ? 0u : n8;         // 8 x the cell this lane has reached
         uint32_t prev = 0xffffffffu;                     // interval of the last pe of the group before
         uint32_t warp_done = 0;
@@ -427,27 +433,29 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
         };
 
         while (true) {
-            if (nq == 4) {
-                // queue empty: the next four pe (three Philox blocks: gaps, cluster sizes, two Box-Muller pairs)
-                const u32x4 rg = nsb_block(3u * grp);
-                const u32x4 rb = nsb_block(3u * grp + 1u);
-                const u32x4 rn = nsb_block(3u * grp + 2u);
-                ++grp;
-                float z0, z1, z2, z3;
-                normal_pair(rn.x, rn.y, z0, z1);
-                normal_pair(rn.z, rn.w, z2, z3);
-                prev = gq3;
-                make_pe(rg.x, rb.x, z0, gq0, Aq0, vq0);
-                make_pe(rg.y, rb.y, z1, gq1, Aq1, vq1);
-                make_pe(rg.z, rb.z, z2, gq2, Aq2, vq2);
-                make_pe(rg.w, rb.w, z3, gq3, Aq3, vq3);
+            if (nq == NQ) {
+                // queue empty: the next pe, four per three Philox blocks (gaps, cluster sizes, two Box-Muller pairs)
+                prev = gq[NQ - 1];
+#pragma unroll
+                for (int gi = 0; gi < DCT_TC_GROUPS; ++gi) {
+                    const u32x4 rg = nsb_block(3u * grp);
+                    const u32x4 rb = nsb_block(3u * grp + 1u);
+                    const u32x4 rn = nsb_block(3u * grp + 2u);
+                    ++grp;
+                    float z0, z1, z2, z3;
+                    normal_pair(rn.x, rn.y, z0, z1);
+                    normal_pair(rn.z, rn.w, z2, z3);
+                    make_pe(rg.x, rb.x, z0, gq[4 * gi + 0], Aq[4 * gi + 0], vq[4 * gi + 0]);
+                    make_pe(rg.y, rb.y, z1, gq[4 * gi + 1], Aq[4 * gi + 1], vq[4 * gi + 1]);
+                    make_pe(rg.z, rb.z, z2, gq[4 * gi + 2], Aq[4 * gi + 2], vq[4 * gi + 2]);
+                    make_pe(rg.w, rb.w, z3, gq[4 * gi + 3], Aq[4 * gi + 3], vq[4 * gi + 3]);
+                }
                 nq = 0;
-                cur8 = gq0;
+                cur8 = gq[0];
             }
-            store_pe(0, gq0, prev, Aq0, vq0, gq1);
-            store_pe(1, gq1, gq0, Aq1, vq1, gq2);
-            store_pe(2, gq2, gq1, Aq2, vq2, gq3);
-            store_pe(3, gq3, gq2, Aq3, vq3, gq3);
+#pragma unroll
+            for (int k = 0; k < NQ; ++k)
+                store_pe(k, gq[k], k ? gq[k - 1] : prev, Aq[k], vq[k], gq[k + 1 < NQ ? k + 1 : NQ - 1]);
             // publish the cell every lane of this warp has reached
             const uint32_t wmin = __reduce_min_sync(0xffffffffu, cur8) >> 3;
             if (wmin > warp_done) {
@@ -461,7 +469,7 @@ k_generate_tensor(const __grid_constant__ TensorArgs ta) {
             }
             if (wmin >= (uint32_t)n_cells) break;
             limit8 = min((tc::ld_volatile(released) + (uint32_t)RING) * TC_PHASES, n8);
-            if (!__any_sync(0xffffffffu, nq == 4 || cur8 < limit8)) {      // every lane waits for a slot
+            if (!__any_sync(0xffffffffu, nq == NQ || cur8 < limit8)) {      // every lane waits for a slot
                 __nanosleep(32);
                 if (++idle > (1u << 26)) __trap();       // a protocol error fails the launch instead of hanging
             }
