@@ -532,6 +532,33 @@ def test_stats_kernel_synthetic_extremes():
     _check_stats_against_numpy(g, out, charge_lo=-1000, n_charge_bins=5000)
 
 
+@pytest.mark.parametrize('geometry', ['acdc-50-bins', 'dark-92-bins'])
+def test_stats_sums_of_squares_do_not_wrap_on_a_fully_saturated_wide_range_cube(geometry):
+    """the tile kernel keeps a trace's sum of squares in 32 bits.  With saturate=(0, 8191) a
+    fully saturated 92-bin trace holds 92 x 8191^2 = 6.2e9 > 2^32: the host gate must send that cube to
+    the generic kernel; the 50-bin one (3.4e9) still fits the fast path.  Either way: NumPy's numbers."""
+    import torch
+    kw = dict(n_pixels=130, nsb_rate=0.01, seed=1, saturate=(0, 8191))
+    kw.update(ACDC if geometry.startswith('acdc') else DARK)
+    if 'nsb_rate' in DARK and not geometry.startswith('acdc'):
+        kw['nsb_rate'] = 0.003
+    g = gen(**kw)
+    B = g.params.n_bins
+    c = np.full((40, 130, B), 8191, dtype=np.int16)
+    c[::3, ::2] = 8000
+    out = torch.from_numpy(c).cuda()
+    from digicamtoy_b200.stats import CubeStats
+    st = CubeStats(g, charge_lo=0, n_charge_bins=1000)
+    st.accumulate(out)
+    r = st.result()
+    c64 = c.astype(np.int64)
+    assert np.array_equal(r['pixel_sumsq'], (c64 ** 2).sum(axis=(0, 2)))
+    assert np.array_equal(r['bin_sumsq'], (c64 ** 2).sum(axis=(0, 1)))
+    assert np.array_equal(r['pixel_sum'], c64.sum(axis=(0, 2)))
+    assert np.array_equal(r['adc_hist'], np.bincount(c64.ravel(), minlength=8192))
+    assert r['charge_hist'][-1] == 40 * 130                       # every charge beyond the last bin
+
+
 FUSED_CASES = [
     ('sweep-acdc', dict(n_pixels=200, nsb_rate=0.3, n_photon=5., **ACDC), 150, 'sweep'),
     ('sweep-dark-92', dict(n_pixels=130, n_photon=2., **DARK), 200, 'sweep'),
