@@ -346,6 +346,22 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                                       (double)h->tc_n_cells * dct::TC_PHASES);
     }
 
+    // generalised-Poisson tables of the on-grid mode, per pixel, in double (sampling.cuh: gp_table_draw)
+    std::vector<float> f_gp;
+    if (p.sub_binning > 0) {
+        f_gp.assign((size_t)P * dct::GP_TABLE, 1.0f);
+        for (int i = 0; i < P; ++i) {
+            const double lam = c->nsb_rate[i] * c->dt, mu = c->crosstalk[i];
+            if (!(lam > 0.0) || lam >= (double)dct::GP_LAM_MAX) continue;
+            double cdf = 0.0;
+            for (int k = 0; k < dct::GP_TABLE; ++k) {
+                const double a = lam + k * mu;
+                cdf += std::exp(std::log(lam) + (k - 1.0) * std::log(a) - a - std::lgamma(k + 1.0));
+                f_gp[(size_t)i * dct::GP_TABLE + k] = (float)std::min(cdf, 1.0);
+            }
+        }
+    }
+
     // ---- one arena
     size_t cur = 0;
     const size_t o_rate = arena_reserve<float>(cur, P), o_inv = arena_reserve<float>(cur, P),
@@ -361,7 +377,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                  o_kn = arena_reserve<double>(cur, (size_t)n_iv + 1),
                  o_poly = arena_reserve<float>(cur, f_poly.size() + 4),
                  o_grid = arena_reserve<float>(cur, f_grid.size()),
-                 o_tc = arena_reserve<uint16_t>(cur, tc_coef.size());
+                 o_tc = arena_reserve<uint16_t>(cur, tc_coef.size()),
+                 o_gp = arena_reserve<float>(cur, f_gp.size());
     h->arena.size = cur + 256;
     cudaError_t e = cudaMalloc(&h->arena.base, h->arena.size);
     if (e != cudaSuccess) {
@@ -377,7 +394,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     UP(o_rate, f_rate); UP(o_inv, f_inv); UP(o_xt, f_xt); UP(o_exp, f_exp); UP(o_gain, f_gain);
     UP(o_s1, f_s1); UP(o_se, f_se); UP(o_base, f_base); UP(o_dgain, d_gain); UP(o_dbase, d_base);
     UP(o_npe, f_npe); UP(o_tsig, f_tsig); UP(o_jit, f_jit); UP(o_c32, f_coef); UP(o_poly, f_poly);
-    UP(o_grid, f_grid); UP(o_tc, tc_coef);
+    UP(o_grid, f_grid); UP(o_tc, tc_coef); UP(o_gp, f_gp);
 #undef UP
     if (ue == cudaSuccess) ue = up(o_c64, c->coef, (size_t)n_iv * 4 * sizeof(double));
     if (ue == cudaSuccess) ue = up(o_kn, c->knot_x, ((size_t)n_iv + 1) * sizeof(double));
@@ -396,6 +413,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     p.coef32 = (const float4*)(base + o_c32); p.coef64 = (const double*)(base + o_c64);
     p.knots = (const double*)(base + o_kn); p.poly = (const float4*)(base + o_poly);
     p.grid_tap = (const float*)(base + o_grid);
+    p.gp_cdf = f_gp.empty() ? nullptr : (const float*)(base + o_gp);
     h->tc_coef = (const __half*)(base + o_tc);
 
     // ---- kernel selection and launch geometry

@@ -51,6 +51,7 @@ struct DevParams {
     const double* knots;          // [n_iv + 1]
     const float4* poly;           // [n_taps][n_phase]
     const float*  grid_tap;       // [grid_n]
+    const float*  gp_cdf;         // [P][32] cumulative generalised-Poisson probabilities of the on-grid mode (sub_binning > 0), else null
 };
 
 }  // namespace dct

@@ -61,9 +61,15 @@ __global__ void k_dump_pe(const DumpArgs d) {
         } else {
             const float lam = rate * p.dt, p0 = __expf(-lam);
             const int n_sim = p.n_drop + p.B;
+            const bool gp = lam < GP_LAM_MAX && p.gp_cdf != nullptr;
             for (int bs = 0; bs < n_sim; ++bs) {
                 float A;
-                if (!subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) continue;
+                if (gp) {
+                    const u32x4 r = draw_block_rk(a.rk, t.key, STREAM_SUBBIN_GP, (uint32_t)bs >> 1);
+                    if (!subbin_total(r, (uint32_t)bs, lam, q, p.gp_cdf + (size_t)t.pixel * GP_TABLE, 1, A)) continue;
+                } else if (!subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) {
+                    continue;
+                }
                 emit(p.t0_d + (double)bs * p.dt_d, A);
             }
         }

@@ -171,6 +171,27 @@ __device__ __forceinline__ float smeared_amplitude(int n, float z, float sigma1)
     return __fmaf_rn(z * sigma1, fast_sqrt(fn), fn);
 }
 
+// On-grid NSB mode (sub_binning > 0, reference :259-267 + :306-312 + :329-348), one simulated bin, fast
+// form: the total T of primaries and crosstalk progeny from ONE uniform through the pixel's
+// generalised-Poisson table (sampling.cuh), then gain smearing.  Two bins share a Philox block of
+// STREAM_SUBBIN_GP -- block bs / 2:  .x -> T of the even bin, .y -> T of the odd bin, (.z, .w) ->
+// Box-Muller pair, cosine for the even and sine for the odd bin.  `r` is that block (callers that
+// walk the bins in order draw it once per pair).  Returns false for an empty bin.
+// cdf / stride: the pixel's table (global: stride 1; the grid kernel's shared copy: stride NT).
+__device__ __forceinline__ bool subbin_total(const u32x4& r, uint32_t bs, float lam, const PixelNsb& q,
+                                             const float* cdf, int stride, float& A) {
+    const uint32_t w = (bs & 1u) ? r.y : r.x;
+    const int total = gp_table_draw(u01_open1(w), cdf, stride, lam, q.xt);
+    if (total == 0) return false;
+    A = (float)total;
+    if (q.sigma1 > 0.0f) {
+        float z0, z1;
+        normal_pair(r.z, r.w, z0, z1);
+        A = smeared_amplitude(total, (bs & 1u) ? z1 : z0, q.sigma1);
+    }
+    return true;
+}
+
 // On-grid NSB mode (sub_binning > 0, reference :259-267 + :306-312 + :329-348), one simulated bin:
 // n ~ Poisson(lam) pe on the sample, their crosstalk progeny, gain smearing.  Returns false for an
 // empty bin.  Everything comes from Philox block `bs` of STREAM_SUBBIN in the common case, so the
@@ -431,9 +452,15 @@ k_generate_scatter(const GenArgs a) {
                 // on-grid NSB (:259-267): n ~ Poisson(rate dt) pe exactly on every simulated bin
                 const float lam = rate * p.dt, p0 = __expf(-lam);
                 const int n_sim = p.n_drop + B;
+                const bool gp = lam < GP_LAM_MAX && p.gp_cdf != nullptr;
                 for (int bs = 0; bs < n_sim; ++bs) {
                     float A;
-                    if (!subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) continue;
+                    if (gp) {
+                        const u32x4 r = draw_block_rk(a.rk, t.key, STREAM_SUBBIN_GP, (uint32_t)bs >> 1);
+                        if (!subbin_total(r, (uint32_t)bs, lam, q, p.gp_cdf + (size_t)t.pixel * GP_TABLE, 1, A)) continue;
+                    } else if (!subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) {
+                        continue;
+                    }
                     for (int m = 0; m < p.grid_n; ++m) {
                         const int kb = bs + p.grid_m_lo + m - p.n_drop;
                         if (kb >= 0 && kb < B) row[kb] = __fmaf_rn(A, p.grid_tap[m], row[kb]);

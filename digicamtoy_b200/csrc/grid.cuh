@@ -5,8 +5,10 @@
 // the sampling period: a fixed FIR (23 taps for the 88 ns template at 4 ns).  The scatter kernel
 // does that as 23 dependent read-modify-writes of the shared-memory row per bin; here the taps are
 // kernel parameters (constant-bank operands of the FMAs) and the partial sums of the next GRID_TAPS
-// bins live in registers: after simulated bin bs has been drawn, W[0] is final, is retired to the
-// row, and the window moves one bin -- the same for every lane, no predication.
+// bins live in registers: after simulated bin bs has been drawn its own partial sum is final and is
+// retired to the row -- the same for every lane, no predication.  The loop over the bins is unrolled
+// GRID_UNROLL times and the window moves by that many registers per pass; the number of pe on a bin
+// (primaries + crosstalk progeny) comes from one table look-up, two bins share a Philox block.
 //
 // Random numbers and the order of the float32 FMAs into every output bin are those of the scatter
 // kernel's sub_binning branch (generate.cuh), so the two kernels produce identical cubes.
@@ -17,14 +19,18 @@ namespace dct {
 
 constexpr int GRID_TAPS = 24;                // window length; templates with more on-grid taps use K1b
 constexpr int GRID_THREADS = 128;
+#ifndef DCT_GRID_UNROLL
+#define DCT_GRID_UNROLL 2
+#endif
+constexpr int GRID_UNROLL = DCT_GRID_UNROLL;   // simulated bins per pass of the bin loop (even: two bins share a Philox block)
 
 struct GridArgs {
     GenArgs g;
     float tap[GRID_TAPS];                    // h((grid_m_lo + j) * dt), zero beyond grid_n
 };
 
-__host__ __device__ inline size_t grid_smem_bytes(int B) {    // rows + one Poisson table per trace
-    return gen_smem_bytes(B, 0, GRID_THREADS) + (size_t)GRID_THREADS * POISSON_TABLE * sizeof(float);
+__host__ __device__ inline size_t grid_smem_bytes(int B) {    // rows + one table of cumulative probabilities per trace
+    return gen_smem_bytes(B, 0, GRID_THREADS) + (size_t)GRID_THREADS * GP_TABLE * sizeof(float);
 }
 
 __host__ __device__ inline bool grid_supported(const DevParams& p) {
@@ -56,23 +62,63 @@ k_generate_grid(const GridArgs ga) {
         const float rate = p.rate[t.pixel];
         const PixelNsb q = load_pixel_nsb(p, t.pixel);
         if (rate > 0.0f) {
-            float W[GRID_TAPS];                              // W[j] <-> simulated bin bs + grid_m_lo + j
-#pragma unroll
-            for (int j = 0; j < GRID_TAPS; ++j) W[j] = 0.0f;
             const float lam = rate * p.dt, p0 = __expf(-lam);
-            if (lam < 12.0f) poisson_table_fill(cdf, NT, lam, p0);   // (only this thread reads it)
             const int n_sim = p.n_drop + B;
-            int kb = p.grid_m_lo - p.n_drop;                 // kept index of W[0]
-            for (int bs = 0; bs < n_sim; ++bs, ++kb) {
-                float A;
-                if (subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A, cdf, NT)) {
+            const int kb0 = p.grid_m_lo - p.n_drop;          // kept index of the bin retired at simulated bin 0
+            if (lam < GP_LAM_MAX && p.gp_cdf != nullptr) {
+                // the pixel's generalised-Poisson table -> this trace's shared-memory column (stride NT)
+                const float4* src = reinterpret_cast<const float4*>(p.gp_cdf + (size_t)t.pixel * GP_TABLE);
 #pragma unroll
-                    for (int j = 0; j < GRID_TAPS; ++j) W[j] = __fmaf_rn(A, ga.tap[j], W[j]);
+                for (int i = 0; i < GP_TABLE / 4; ++i) {
+                    const float4 c4 = src[i];
+                    cdf[(4 * i + 0) * NT] = c4.x; cdf[(4 * i + 1) * NT] = c4.y;
+                    cdf[(4 * i + 2) * NT] = c4.z; cdf[(4 * i + 3) * NT] = c4.w;
                 }
-                if ((unsigned)kb < (unsigned)B) row[kb] = W[0];
+                // GRID_UNROLL bins per pass of the outer loop: bin bs0 + s adds its taps to V[s + m] (static
+                // indices), then V[s] is final and goes to the row; after the pass the window moves down by
+                // GRID_UNROLL registers at once (GRID_TAPS moves per GRID_UNROLL bins instead of per bin).
+                // A pass is short enough for the instruction cache; unrolling all GRID_TAPS bins (pure
+                // renaming, no moves) was measured: 39 % issue, stalled on instruction fetch.
+                // Same FMAs in the same order into every output bin as the scatter kernel.
+                float V[GRID_TAPS + GRID_UNROLL - 1];
 #pragma unroll
-                for (int j = 0; j < GRID_TAPS - 1; ++j) W[j] = W[j + 1];
-                W[GRID_TAPS - 1] = 0.0f;
+                for (int j = 0; j < GRID_TAPS + GRID_UNROLL - 1; ++j) V[j] = 0.0f;
+                u32x4 r = {0u, 0u, 0u, 0u};
+                for (int bs0 = 0; bs0 < n_sim; bs0 += GRID_UNROLL) {
+#pragma unroll
+                    for (int s = 0; s < GRID_UNROLL; ++s) {
+                        const int bs = bs0 + s;
+                        if (bs < n_sim) {                    // (uniform across the CTA)
+                            if ((s & 1) == 0) r = draw_block_rk(a.rk, t.key, STREAM_SUBBIN_GP, (uint32_t)bs >> 1);
+                            float A = 0.0f;
+                            subbin_total(r, (uint32_t)bs, lam, q, cdf, NT, A);
+#pragma unroll
+                            for (int m = 0; m < GRID_TAPS; ++m) V[s + m] = __fmaf_rn(A, ga.tap[m], V[s + m]);
+                            const int kb = bs + kb0;
+                            if ((unsigned)kb < (unsigned)B) row[kb] = V[s];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < GRID_TAPS + GRID_UNROLL - 1; ++j)
+                        V[j] = (j + GRID_UNROLL < GRID_TAPS + GRID_UNROLL - 1) ? V[j + GRID_UNROLL] : 0.0f;
+                }
+            } else {
+                // rate * dt >= 12 (3 GHz at 4 ns): primaries by PTRS, crosstalk generation by generation
+                float W[GRID_TAPS];                          // partial sums of the next GRID_TAPS simulated bins
+#pragma unroll
+                for (int j = 0; j < GRID_TAPS; ++j) W[j] = 0.0f;
+                int kb = kb0;
+                for (int bs = 0; bs < n_sim; ++bs, ++kb) {
+                    float A;
+                    if (subbin_cluster(t.key, (uint32_t)bs, lam, p0, q, A)) {
+#pragma unroll
+                        for (int j = 0; j < GRID_TAPS; ++j) W[j] = __fmaf_rn(A, ga.tap[j], W[j]);
+                    }
+                    if ((unsigned)kb < (unsigned)B) row[kb] = W[0];
+#pragma unroll
+                    for (int j = 0; j < GRID_TAPS - 1; ++j) W[j] = W[j + 1];
+                    W[GRID_TAPS - 1] = 0.0f;
+                }
             }
             // what is left in the window belongs to bins past the end of the trace
         }

@@ -23,7 +23,8 @@ enum : uint32_t {
     STREAM_SIGNAL   = 1u,   // block k -> jitter / smearing of signal pulse k
     STREAM_BRANCH   = 2u,   // variable-length: Poisson(n_photon) and crosstalk generations of the pulses
     STREAM_NOISE    = 3u,   // block q -> electronic noise of kept bins 4q..4q+3
-    STREAM_SUBBIN   = 4u,   // on-grid NSB mode (sub_binning > 0): block bs -> simulated bin bs; (bs+1)<<16.. overflow
+    STREAM_SUBBIN   = 4u,   // on-grid NSB mode, rate * dt >= 12: block bs -> simulated bin bs; (bs+1)<<16.. overflow
+    STREAM_SUBBIN_GP = 5u,  // on-grid NSB mode (sub_binning > 0): block m -> simulated bins 2m, 2m+1 (total pe, normals)
 };
 
 __host__ __device__ __forceinline__ u32x4 philox4x32(u32x4 c, uint32_t k0, uint32_t k1) {

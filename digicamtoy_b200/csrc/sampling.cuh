@@ -197,6 +197,41 @@ __device__ __forceinline__ int poisson_table_draw(float u, const float* cdf, int
     return k;
 }
 
+// ---- On-grid NSB mode: the total number of pe on one sample = Poisson(lam) primaries plus their
+// Galton-Watson crosstalk progeny (Poisson(mu) offspring), i.e. the generalised Poisson law
+//     P(T = k) = lam (lam + k mu)^(k-1) e^(-lam - k mu) / k!          (reference utils/pdf.py:37-42;
+// what generate_nsb :259-267 followed by generate_crosstalk :306-312 leaves on a sample).
+// Sampled by inversion of ONE uniform in a per-pixel table of the first GP_TABLE cumulative
+// probabilities, computed in double by dct_create; beyond the table (P ~ 1e-9 at 1 GHz, xt 0.08)
+// the recurrence carries on in float.
+constexpr int GP_TABLE = 32;
+constexpr float GP_LAM_MAX = 12.0f;      // pixels with rate * dt at or above it keep the generation-by-generation sampler
+
+__device__ __noinline__ int gp_tail(float u, float lam, float mu, float cdf_last) {
+    float cdf = cdf_last;
+    const float ln_lam = logf(lam);
+    for (int k = GP_TABLE; k < 4096; ++k) {
+        const float fk = (float)k, a = fmaf(mu, fk, lam);
+        const float p = expf(ln_lam + (fk - 1.0f) * logf(a) - a - lgammaf(fk + 1.0f));
+        const float next = cdf + p;
+        if (next == cdf) return k;                 // tail below float resolution (see borel_search)
+        cdf = next;
+        if (u < cdf) return k;
+    }
+    return 4096;
+}
+
+// T = min { k : u < cdf[k] }; cdf[i * stride] = P(T <= i), non-decreasing, i < GP_TABLE.
+__device__ __forceinline__ int gp_table_draw(float u, const float* cdf, int stride, float lam, float mu) {
+    int k = (u >= cdf[15 * stride]) ? 16 : 0;
+    k += (u >= cdf[(k + 7) * stride]) ? 8 : 0;
+    k += (u >= cdf[(k + 3) * stride]) ? 4 : 0;
+    k += (u >= cdf[(k + 1) * stride]) ? 2 : 0;
+    k += (u >= cdf[k * stride]) ? 1 : 0;
+    if (k == GP_TABLE - 1 && u >= cdf[(GP_TABLE - 1) * stride]) k = gp_tail(u, lam, mu, cdf[(GP_TABLE - 1) * stride]);
+    return k;
+}
+
 // On-grid NSB mode, one simulated bin: the part of the count that the bin's own Philox block could
 // not provide (see subbin_cluster in generate.cuh) -- a Poisson mean >= 12 (PTRS needs a variable
 // number of uniforms) or a crosstalk chain that outlived the draws set aside for it.  Reads from

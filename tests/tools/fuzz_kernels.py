@@ -1,5 +1,5 @@
 """Randomised cross-checks of the generation kernels (GPU): for random configurations
-   * sweep == scatter bit for bit (where the sweep kernel applies),
+   * sweep == scatter bit for bit (where the sweep kernel applies), grid == scatter in the on-grid mode,
    * tensor within 1 LSB of sweep on a small share of samples (where the tensor kernel applies),
    * fused statistics == separate statistics == NumPy,
    * chunked generation == one-shot generation.
@@ -26,6 +26,10 @@ def random_config(rs):
               sigma_e=float(rs.choice([0.0, 0.8, 1.25])), sigma_1=float(rs.choice([0.0, 0.8])), gain=float(rs.uniform(2, 8)),
               baseline=float(rs.choice([0, 10.4, 200, 500])), time_signal=float(time_start + rs.uniform(-10, n_bins * dt)),
               jitter=float(rs.choice([0.0, 0.3, 2.0])), n_photon=float(rs.choice([0, 0, 1, 10, 300, 3000])))
+    if rs.rand() < 0.2:
+        kw['sub_binning'] = 1                      # on-grid NSB mode: grid kernel against the scatter kernel
+        if rs.rand() < 0.15 and not isinstance(rate, list):
+            kw['nsb_rate'] = float(rs.uniform(3.0, 4.0))   # rate * dt >= 12: the generation-by-generation sampler
     return kw
 
 
@@ -37,7 +41,7 @@ def run_case(i, rs):
                                                           'per-pixel' if isinstance(kw['nsb_rate'], list) else '%.4g' % kw['nsb_rate'],
                                                           kw['n_photon'], kw['crosstalk'])
     gens = {}
-    for k in ('scatter', 'sweep', 'tensor', 'auto'):
+    for k in ('scatter', 'sweep', 'tensor', 'grid', 'auto'):
         try:
             gens[k] = NTraceGenerator(seed=seed, kernel=k, **kw)
         except ValueError as e:
@@ -50,6 +54,8 @@ def run_case(i, rs):
     ref = cubes['scatter']
     if 'sweep' in cubes:
         assert torch.equal(ref, cubes['sweep']), tag + ': sweep != scatter'
+    if 'grid' in cubes:
+        assert torch.equal(ref, cubes['grid']), tag + ': grid != scatter'
     if 'tensor' in cubes:
         d = (cubes['tensor'].int() - ref.int())
         g0 = gens['scatter']
