@@ -362,6 +362,26 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         }
     }
 
+    // ... and of the small signal pulses (Poisson(n_photon) primaries + their crosstalk progeny), per pixel and pulse
+    std::vector<float> f_sig_gp;
+    if (c->poisson) {
+        bool any_small = false;
+        for (size_t i = 0; i < (size_t)P * K; ++i) any_small |= c->n_photon[i] > 0.0 && c->n_photon[i] < (double)dct::GP_LAM_MAX;
+        if (any_small) {
+            f_sig_gp.assign((size_t)P * K * dct::GP_TABLE, 1.0f);
+            for (size_t i = 0; i < (size_t)P * K; ++i) {
+                const double lam = (double)(float)c->n_photon[i], mu = c->crosstalk[i / K];
+                if (!(lam > 0.0) || lam >= (double)dct::GP_LAM_MAX) continue;
+                double cdf = 0.0;
+                for (int k = 0; k < dct::GP_TABLE; ++k) {
+                    const double a = lam + k * mu;
+                    cdf += std::exp(std::log(lam) + (k - 1.0) * std::log(a) - a - std::lgamma(k + 1.0));
+                    f_sig_gp[i * dct::GP_TABLE + k] = (float)std::min(cdf, 1.0);
+                }
+            }
+        }
+    }
+
     // ---- one arena
     size_t cur = 0;
     const size_t o_rate = arena_reserve<float>(cur, P), o_inv = arena_reserve<float>(cur, P),
@@ -378,7 +398,8 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
                  o_poly = arena_reserve<float>(cur, f_poly.size() + 4),
                  o_grid = arena_reserve<float>(cur, f_grid.size()),
                  o_tc = arena_reserve<uint16_t>(cur, tc_coef.size()),
-                 o_gp = arena_reserve<float>(cur, f_gp.size());
+                 o_gp = arena_reserve<float>(cur, f_gp.size()),
+                 o_sgp = arena_reserve<float>(cur, f_sig_gp.size());
     h->arena.size = cur + 256;
     cudaError_t e = cudaMalloc(&h->arena.base, h->arena.size);
     if (e != cudaSuccess) {
@@ -394,7 +415,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     UP(o_rate, f_rate); UP(o_inv, f_inv); UP(o_xt, f_xt); UP(o_exp, f_exp); UP(o_gain, f_gain);
     UP(o_s1, f_s1); UP(o_se, f_se); UP(o_base, f_base); UP(o_dgain, d_gain); UP(o_dbase, d_base);
     UP(o_npe, f_npe); UP(o_tsig, f_tsig); UP(o_jit, f_jit); UP(o_c32, f_coef); UP(o_poly, f_poly);
-    UP(o_grid, f_grid); UP(o_tc, tc_coef); UP(o_gp, f_gp);
+    UP(o_grid, f_grid); UP(o_tc, tc_coef); UP(o_gp, f_gp); UP(o_sgp, f_sig_gp);
 #undef UP
     if (ue == cudaSuccess) ue = up(o_c64, c->coef, (size_t)n_iv * 4 * sizeof(double));
     if (ue == cudaSuccess) ue = up(o_kn, c->knot_x, ((size_t)n_iv + 1) * sizeof(double));
@@ -414,6 +435,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     p.knots = (const double*)(base + o_kn); p.poly = (const float4*)(base + o_poly);
     p.grid_tap = (const float*)(base + o_grid);
     p.gp_cdf = f_gp.empty() ? nullptr : (const float*)(base + o_gp);
+    p.sig_cdf = f_sig_gp.empty() ? nullptr : (const float*)(base + o_sgp);
     h->tc_coef = (const __half*)(base + o_tc);
 
     // ---- kernel selection and launch geometry

@@ -45,6 +45,7 @@ struct DevParams {
     const float* npe;
     const float* tsig;
     const float* jitter;
+    const float* sig_cdf;         // [P, K][32] generalised-Poisson tables of the small pulses (poisson, 0 < n_photon < 12), else null
     // template tables
     const float4* coef32;         // [n_iv]  (c0, c1, c2, c3)
     const double* coef64;         // [n_iv][4]

@@ -268,9 +268,17 @@ __device__ __forceinline__ void add_signal_pulses(const GenArgs& a, const TraceI
         const u32x4 r = draw_block(t.key, STREAM_SIGNAL, (uint32_t)k);
         if (jit > 0.0f) ts += (u01_open1(r.x) - 0.5f) * jit;             // U(-j/2, j/2)  (:233)
         if (npe > 0.0f) {
-            BlockReader rd(t.key, STREAM_BRANCH, (uint32_t)k << 20);
-            const int n0 = p.poisson ? poisson(rd, npe) : (int)rintf(npe);
-            const int total = branching_total(rd, n0, xt);
+            int total;
+            if (p.sig_cdf != nullptr && p.poisson && npe < GP_LAM_MAX) {
+                // small pulses (every level of dark.yml, n_photon 1 and 10 of ac_dc.yml): primaries and
+                // crosstalk progeny in one inversion of the block's fourth word through the pulse's
+                // generalised-Poisson table -- same law as Poisson(n_photon) + one tree per primary
+                total = gp_table_scan(u01_open1(r.w), p.sig_cdf + (size_t)(t.pixel * p.K + k) * GP_TABLE, npe, xt);
+            } else {
+                BlockReader rd(t.key, STREAM_BRANCH, (uint32_t)k << 20);
+                const int n0 = p.poisson ? poisson(rd, npe) : (int)rintf(npe);
+                total = branching_total(rd, n0, xt);
+            }
             A = (float)total;
             if (total > 0 && sigma1 > 0.0f) A = smeared_amplitude(total, normal_one(r.y, r.z), sigma1);
         }

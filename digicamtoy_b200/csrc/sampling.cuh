@@ -197,6 +197,20 @@ __device__ __forceinline__ int poisson_table_draw(float u, const float* cdf, int
     return k;
 }
 
+constexpr int GP_TABLE_ENTRIES = 32;
+__device__ int gp_tail_entry(float u, float lam, float mu, float cdf_last);
+
+// The same look-up for tables that stay in global memory (one per pixel and pulse): a linear scan
+// in 16-byte pieces, most draws end in the first one or two.  Same result as gp_table_draw.
+__device__ __forceinline__ int gp_table_scan(float u, const float* cdf, float lam, float mu) {
+    const float4* c4 = reinterpret_cast<const float4*>(cdf);
+    for (int i = 0; i < GP_TABLE_ENTRIES / 4; ++i) {
+        const float4 v = c4[i];
+        if (u < v.w) return 4 * i + (u >= v.x) + (u >= v.y) + (u >= v.z);
+    }
+    return gp_tail_entry(u, lam, mu, cdf[GP_TABLE_ENTRIES - 1]);
+}
+
 // ---- On-grid NSB mode: the total number of pe on one sample = Poisson(lam) primaries plus their
 // Galton-Watson crosstalk progeny (Poisson(mu) offspring), i.e. the generalised Poisson law
 //     P(T = k) = lam (lam + k mu)^(k-1) e^(-lam - k mu) / k!          (reference utils/pdf.py:37-42;
@@ -204,7 +218,7 @@ __device__ __forceinline__ int poisson_table_draw(float u, const float* cdf, int
 // Sampled by inversion of ONE uniform in a per-pixel table of the first GP_TABLE cumulative
 // probabilities, computed in double by dct_create; beyond the table (P ~ 1e-9 at 1 GHz, xt 0.08)
 // the recurrence carries on in float.
-constexpr int GP_TABLE = 32;
+constexpr int GP_TABLE = GP_TABLE_ENTRIES;
 constexpr float GP_LAM_MAX = 12.0f;      // pixels with rate * dt at or above it keep the generation-by-generation sampler
 
 __device__ __noinline__ int gp_tail(float u, float lam, float mu, float cdf_last) {
@@ -220,6 +234,8 @@ __device__ __noinline__ int gp_tail(float u, float lam, float mu, float cdf_last
     }
     return 4096;
 }
+
+__device__ __forceinline__ int gp_tail_entry(float u, float lam, float mu, float cdf_last) { return gp_tail(u, lam, mu, cdf_last); }
 
 // T = min { k : u < cdf[k] }; cdf[i * stride] = P(T <= i), non-decreasing, i < GP_TABLE.
 __device__ __forceinline__ int gp_table_draw(float u, const float* cdf, int stride, float lam, float mu) {

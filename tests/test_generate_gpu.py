@@ -243,6 +243,30 @@ def test_branching_total_is_generalised_poisson(n0, xt):
         assert np.all(np.abs(obs - pmf[:5] * s.size) < 5 * np.sqrt(pmf[:5] * s.size) + 1)
 
 
+@pytest.mark.parametrize('npe,xt', [(0.5, 0.0), (3.0, 0.08), (11.9, 0.08), (2.0, 0.4), (10.0, 0.3)])
+def test_small_pulses_follow_the_generalised_poisson_law(npe, xt):
+    """Pulses with n_photon < 12 take primaries + crosstalk progeny from one inversion in a
+    generalised-Poisson table (reference: Poisson(n_photon) :236, one Galton-Watson tree per primary
+    :319-324; closed form utils/pdf.py:37-42).  With sigma_1 = 0 the truth charge IS that total."""
+    from scipy.special import gammaln
+    g = gen(n_pixels=512, nsb_rate=0.0, n_photon=npe, crosstalk=xt, sigma_1=0.0, seed=33)
+    _, _, q = cube(g, 800, truth=True)
+    tot = q.ravel()
+    assert np.array_equal(tot, np.round(tot)) and tot.min() >= 0
+    k = np.arange(0, 200)
+    with np.errstate(divide='ignore'):
+        logp = np.log(npe) + (k - 1) * np.log(npe + k * xt) - (npe + k * xt) - gammaln(k + 1)
+    pmf = np.exp(logp)
+    assert abs(pmf.sum() - 1) < 1e-9
+    obs = np.bincount(tot.astype(int), minlength=200)[:200].astype(float)
+    keep = pmf * tot.size >= 10
+    chi2 = ((obs[keep] - pmf[keep] * tot.size) ** 2 / (pmf[keep] * tot.size)).sum()
+    rest_obs, rest_exp = obs[~keep].sum(), pmf[~keep].sum() * tot.size
+    chi2 += (rest_obs - rest_exp) ** 2 / max(rest_exp, 1e-9) if rest_exp > 5 else 0.0
+    assert sps.chi2.sf(chi2, keep.sum()) > 1e-3, (chi2, keep.sum())
+    assert tot.mean() == pytest.approx(npe / (1 - xt), rel=4 * np.sqrt(npe / (1 - xt) ** 3 / tot.size) / (npe / (1 - xt)) + 1e-9)
+
+
 # ------------------------------------------------------------------ moments vs closed form
 def _moment_check(kw, n_events, kernel='auto', var_tol=0.03):
     P = kw['n_pixels']
