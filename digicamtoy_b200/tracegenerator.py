@@ -51,9 +51,10 @@ class PinnedPool:
     """Page-locked host buffers, reused: pinning costs ~0.3 ms per MB, more than generating the data
     it will hold (a 238 MB dark.yml level: ~80 ms to pin, 20 ms to generate and copy)."""
 
-    def __init__(self):
+    def __init__(self, max_bytes=16 << 30):
         import threading
         self._free, self._lock = {}, threading.Lock()
+        self.max_bytes, self._held = int(max_bytes), 0       # idle buffers kept; more than that is handed back to the OS
 
     def acquire(self, shape, dtype):
         torch = _torch()
@@ -63,6 +64,8 @@ class PinnedPool:
         with self._lock:
             stack = self._free.get((n, dtype))
             buf = stack.pop() if stack else None
+            if buf is not None:
+                self._held -= buf.numel() * buf.element_size()
         if buf is None:
             buf = torch.empty(n, dtype=dtype).pin_memory()
         return buf.view(*shape)
@@ -70,12 +73,17 @@ class PinnedPool:
     def release(self, *tensors):
         with self._lock:
             for t in tensors:
-                if t is not None:
+                if t is None:
+                    continue
+                nbytes = t.numel() * t.element_size()
+                if self._held + nbytes <= self.max_bytes:
                     self._free.setdefault((t.numel(), t.dtype), []).append(t.reshape(-1))
+                    self._held += nbytes
 
     def clear(self):
         with self._lock:
             self._free.clear()
+            self._held = 0
 
 
 PINNED = PinnedPool()
