@@ -128,7 +128,10 @@ k_stats(const StatsArgs a) {
 #endif                        // the extra resident CTAs pay more than the private columns lose (dark 3.36 -> 2.45 ms)
 constexpr int STATS_WIN = DCT_STATS_WIN;
 constexpr int STATS_ROWS = 128;               // traces per tile = threads per CTA
-constexpr int STATS_CHARGE_WIN = 1024;        // CTA-private window of the charge histogram
+#ifndef DCT_STATS_CHARGE_WIN
+#define DCT_STATS_CHARGE_WIN 1024
+#endif
+constexpr int STATS_CHARGE_WIN = DCT_STATS_CHARGE_WIN;   // CTA-private window of the charge histogram
 #ifndef DCT_STATS_SETS
 #define DCT_STATS_SETS 1      // 2: separate column sets for the low and the high half-word of a cube word (two independent
 #endif                        //    read-modify-write chains per thread)
@@ -167,7 +170,9 @@ __device__ __noinline__ void hist_outside(HistOutside& o, unsigned long long* ad
 
 __global__ void __launch_bounds__(STATS_ROWS)
 k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
-             int hist_lo, int n_hist_s, int single_tile) {
+             int hist_lo, int n_hist_s, int single_tile, int n_charge_s) {
+    // n_charge_s: size of the CTA window of the charge histogram (<= STATS_CHARGE_WIN; the host picks a
+    // small one for quiet cubes: less shared memory, one more CTA per SM)
     // hist_lo / n_hist_s: the slice [hist_lo, hist_lo + n_hist_s) of the ADC range that the CTA
     // histogram covers (the whole range for short traces; for long ones a window, so that more CTAs
     // fit on an SM -- samples outside it go straight to the global histogram).  single_tile: one
@@ -180,11 +185,11 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
     unsigned int* tile1 = single_tile ? tile0 : smem_u + tile_words;
     unsigned int* hist_s = tile1 + tile_words;                  // [n_hist_s]
     unsigned int* charge_s = hist_s + n_hist_s;                 // [STATS_CHARGE_WIN]
-    unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + STATS_CHARGE_WIN);
+    unsigned short* priv_all = reinterpret_cast<unsigned short*>(charge_s + n_charge_s);
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     unsigned short* priv = priv_all + wib * (STATS_WIN * 32) + lane;      // my column: priv[w * 32]
     unsigned short* priv_hi = priv + (STATS_SETS - 1) * (STATS_ROWS / 32) * STATS_WIN * 32;   // second set (or the same)
-    for (int i = tid; i < n_hist_s + STATS_CHARGE_WIN + STATS_PRIV_WORDS; i += STATS_ROWS)
+    for (int i = tid; i < n_hist_s + n_charge_s + STATS_PRIV_WORDS; i += STATS_ROWS)
         hist_s[i] = 0u;
     __syncthreads();
 
@@ -305,7 +310,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
                     const long long cw = bin - charge_win_lo;
                     if (bin >= a.n_charge_bins - 1) ++n_charge_over;
                     else if (bin <= 0) ++n_charge_under;
-                    else if (cw >= 0 && cw < STATS_CHARGE_WIN) atomicAdd(&charge_s[cw], 1u);
+                    else if (cw >= 0 && cw < n_charge_s) atomicAdd(&charge_s[cw], 1u);
                     else atomicAdd(a.charge_hist + bin, 1ull);
                 }
             }
@@ -353,7 +358,7 @@ k_stats_tile(const StatsArgs a, int win_lo, int n_slices, int charge_win_lo,
         __syncthreads();
     }
     if (a.charge_hist)
-        for (int i = tid; i < STATS_CHARGE_WIN; i += STATS_ROWS) {
+        for (int i = tid; i < n_charge_s; i += STATS_ROWS) {
             const unsigned int c = charge_s[i];
             if (c && charge_win_lo + i < a.n_charge_bins) atomicAdd(a.charge_hist + charge_win_lo + i, (unsigned long long)c);
         }
