@@ -757,11 +757,11 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
         // the charge of a trace that holds nothing but that pedestal shift
         const int win_lo = stats_win_lo(h, dct::STATS_WIN);
-        // Quiet cubes (no pulse taller than ~100 LSB: dark runs, NSB-only levels) keep everything within
+        // Quiet cubes (no pulse taller than ~100 LSB and an NSB pedestal shift below 3 LSB: dark runs) keep everything within
         // a few hundred values of the pedestal: a 512-value histogram slice and a 256-bin charge window
         // leave room for one more CTA per SM (measured on dark.yml: 2.45 -> 2.20 ms per 16384 events; the
         // same sizes on C4, whose pulses reach the rail, cost 10 %: 1.91 -> 2.13 ms).
-        const bool quiet = h->max_pulse_lsb < 100.0;
+        const bool quiet = h->max_pulse_lsb < 100.0 && (h->mean_true_baseline - h->mean_baseline) < 3.0;   // and hardly any NSB
         const int n_charge_s = quiet ? std::min(256, dct::STATS_CHARGE_WIN) : dct::STATS_CHARGE_WIN;
         const int compact_hist = quiet ? std::min(512, DCT_STATS_COMPACT_HIST) : DCT_STATS_COMPACT_HIST;
         const double q0 = a.B * (h->mean_true_baseline - h->mean_baseline) - (double)charge_lo;
