@@ -320,7 +320,9 @@ def run_b200_arm(a):
             if ceiling:
                 gbps = e2e['value'] * 2 / 1e9
                 e2e.update(GBps=gbps, plain_copy_ceiling_GBps=ceiling, frac_of_ceiling=gbps / ceiling,
-                           bound='host ingest: PCIe link at N = 1, the box\'s aggregate host path beyond (profiles/r02/host_path.txt)')
+                           bound='host ingest: PCIe link at N = 1, the box\'s aggregate host path beyond.  The ceiling is what N plain D2H copies '
+                                 'reached on one of the pool\'s 8-GPU boxes (profiles/r02/host_path.txt); it varies by box (a 2-GPU box '
+                                 'gave 87 GB/s at N = 2), so the fraction can exceed 1')
         del host
     # ---- the reference's own way of consuming the generator: `for event in generator`
     # (reference produce_data.py:119-126), one event at a time out of prefetched pinned batches
