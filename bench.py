@@ -358,11 +358,13 @@ def run_b200_arm(a):
     k_ms = sum(kernel_ms) / len(kernel_ms)
     algo_bytes = E * P * B * 2
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    traffic, sm_bound = None, None
+    traffic, sm_bound, kernel_name = None, None, 'k_generate_' + gen.kernel
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         tj = json.load(open(tpath)).get(gen.kernel)
         if tj:
+            if not a.fused_stats:          # (with fused statistics K1t runs as the CTA kernel)
+                kernel_name = tj.get('kernel_name', kernel_name)
             per_sample = tj.get(a.workload, tj)['dram_bytes_per_sample'] if a.workload != 'c4' else tj['dram_bytes_per_sample']
             traffic = per_sample * E * P * B
             if a.workload == 'c4' and 'sm_issue_active_pct' in tj:
@@ -372,7 +374,7 @@ def run_b200_arm(a):
                                 active_threads_per_warp_inst=tj['active_threads_per_warp_inst'],
                                 source=tj.get('ncu'))
     roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                    traffic=traffic, kernel='k_generate_' + gen.kernel, kernel_ms=k_ms, sm_bound=sm_bound,
+                    traffic=traffic, kernel=kernel_name, kernel_ms=k_ms, sm_bound=sm_bound,
                     algorithmic_bytes_per_launch=algo_bytes, peak_source=peak_src,
                     note='HBM-write roofline (2 B/sample). This workload is SM-issue-bound, not HBM-bound: '
                          '~245 photo-electron clusters per trace x 22 template taps; see DESIGN.md')
@@ -389,8 +391,8 @@ def run_b200_arm(a):
                 events_per_s=value / (P * B), roofline=roofline, e2e=e2e, iterator=iterator,
                 iterator_events_per_s=iterator['events_per_s'] if iterator else None,
                 gpu_launches=(2 if (not a.fused_stats) else 1) * a.steps,
-                gpu_launches_detail=('per step: 1 x k_generate_%s + 1 x k_stats_tile' if (not a.fused_stats) else
-                                     'per step: 1 x k_generate_%s (statistics fused)') % gen.kernel,
+                gpu_launches_detail=('per step: 1 x %s + 1 x k_stats_tile' % kernel_name if (not a.fused_stats) else
+                                     'per step: 1 x k_generate_%s (statistics fused)' % gen.kernel),
                 clocks=clocks.summary(w0, w1),
                 validation=dict(mean_adc=stats_result['moments'][0] / max(1, stats_result['n_events'] * P * B),
                                 n_events_reduced=stats_result['n_events'],

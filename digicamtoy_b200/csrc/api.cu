@@ -65,6 +65,7 @@ struct DeviceArena {
 struct dct_handle {
     int device = 0;
     int sm_count = 148;
+    int smem_optin = 0;                // largest dynamic shared memory of one CTA [bytes]
     dct::DevParams p{};
     DeviceArena arena;
     int kernel = DCT_KERNEL_SCATTER;
@@ -81,6 +82,7 @@ struct dct_handle {
     // tensor-core kernel (K1t): coefficient tiles live in the arena
     const __half* tc_coef = nullptr;
     int tc_n_cells = 0, tc_col_shift = 0, tc_col0 = 16, tc_n_cells32 = 0;
+    int tc_mega_groups = 0, tc_mega_n_cells32 = 0;     // persistent kernel: groups per SM (0: CTA kernel), its N = 32 cells
     float tc_v_scale = 0.0f;
     int tc_check_span = 1;
     float tc_y0 = 0.0f, tc_y_end = 0.0f;
@@ -209,6 +211,7 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
     if (!h) return fail(DCT_E_NOMEM, "out of host memory");
     h->device = device;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 
     const int P = (int)c->n_pixels, K = (int)c->n_pulses, n_iv = (int)c->n_knots - 1;
     dct::DevParams& p = h->p;
@@ -344,6 +347,17 @@ int dct_create(const dct_config* c, int device, dct_handle** out) {
         const dct::TensorLayout lay = dct::tensor_layout(p.B, p.n_drop, p.cell0, h->tc_n_cells);
         tensor_ok = lay.ok;
         h->tc_col_shift = lay.col_shift; h->tc_col0 = lay.col0; h->tc_n_cells32 = lay.n_cells32;
+        // persistent kernel: five groups per SM when the window fits 102 accumulator columns, else four
+        const dct::TensorLayout lay5 = dct::tensor_layout(p.B, p.n_drop, p.cell0, h->tc_n_cells, dct::TC_MEGA_COLS5);
+        const bool fits5 = lay5.ok && lay5.col0 + ((p.B + 15) / 16) * 16 <= dct::TC_MEGA_COLS5 &&
+                           dct::tensor_mega_smem_bytes(p.B, 5, 5) <= (size_t)h->smem_optin;
+        h->tc_mega_groups = fits5 ? 5 : (dct::tensor_mega_smem_bytes(p.B, 6, 4) <= (size_t)h->smem_optin ? 4 : 0);
+        h->tc_mega_n_cells32 = fits5 ? lay5.n_cells32 : lay.n_cells32;
+        const char* mega_env = getenv("DCT_TENSOR_MEGA");
+        if (mega_env ? atoi(mega_env) == 0 : !DCT_TC_MEGA) h->tc_mega_groups = 0;
+        if (mega_env && atoi(mega_env) == 4 && h->tc_mega_groups == 5) {       // A/B: four groups, six slots
+            h->tc_mega_groups = 4; h->tc_mega_n_cells32 = lay.n_cells32;
+        }
         h->tc_v_scale = (float)(2.0 / dx);
         // the cell test ends the pe stream by itself when the useful cells end a cell before the window
         h->tc_check_span = ((double)n_useful + 1.0) * c->dt <= (double)p.off0 + (c->t_end - c->t0) ? 0 : 1;
@@ -549,6 +563,11 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
         ta.col0 = h->tc_col0; ta.n_cells32 = h->tc_n_cells32;
         ta.check_span = h->tc_check_span;
         ta.y0 = h->tc_y0; ta.y_end = h->tc_y_end;
+        // the persistent kernel has no fused statistics: those launches take the CTA kernel
+        if (h->tc_mega_groups && !(stats && stats->adc_hist)) {
+            ta.n_cells32 = h->tc_mega_n_cells32;
+            return dct::launch_tensor_mega(h->device, h->sm_count, h->tc_mega_groups, ta, st, g_err, sizeof(g_err));
+        }
         return dct::launch_tensor(h->device, ta, st, g_err, sizeof(g_err));
     }
     if (h->kernel == DCT_KERNEL_GRID) return dct::launch_grid(h->device, a, h->grid_tap, st, g_err, sizeof(g_err));
@@ -601,6 +620,18 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
         // chunk ~64 MiB: large enough to amortise launches, small enough to pipeline
         free_pipeline(h);                      // nothing half-built survives a failed earlier attempt
         uint32_t ce = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / trace_bytes);
+        if (h->kernel == DCT_KERNEL_TENSOR && h->tc_mega_groups) {
+            // The persistent kernel hands every group of every SM the same number of 128-trace items
+            // (+-1): take the chunk, up to 20 % smaller, that wastes the least of the last round.
+            const uint64_t slots = (uint64_t)h->sm_count * h->tc_mega_groups;
+            double best = -1.0;
+            const uint32_t n_hi = ce, n_lo = std::max<uint32_t>(1, ce - ce / 5);
+            for (uint32_t n = n_hi; n >= n_lo; --n) {
+                const uint64_t items = ((uint64_t)n * h->p.P + dct::TC_TRACES - 1) / dct::TC_TRACES;
+                const double eff = (double)items / (double)(((items + slots - 1) / slots) * slots);
+                if (eff > best + 1e-9) { best = eff; ce = n; }
+            }
+        }
         h->chunk_events = ce;
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);

@@ -339,9 +339,9 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const RoundKe
 
 // Coalesced store of the CTA's contiguous run of the cube: 16-byte streaming stores gathered from
 // the packed rows.  Output 32-bit word w of the run lives in row w / (B/2), word w % (B/2).
+// (tid: index within the NT threads that store this run)
 template <int NT>
-__device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const float* rows) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const float* rows, const int tid) {
     const int B = a.p.B, SB = row_stride(B);
     const uint64_t left = a.n_traces - trace0;
     const int n_live = (int)(left < (uint64_t)NT ? left : (uint64_t)NT);
@@ -378,6 +378,11 @@ __device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, con
             dst[e] = halves[r * SB * 2 + (e - r * B)];
         }
     }
+}
+
+template <int NT>
+__device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const float* rows) {
+    store_run<NT>(a, trace0, rows, (int)threadIdx.x);
 }
 
 __device__ __forceinline__ PixelNsb load_pixel_nsb(const DevParams& p, int pixel) {

@@ -139,6 +139,37 @@ def test_tensor_kernel_window_shapes(window):
     assert a.float().std() > 1.0
 
 
+@pytest.mark.parametrize('window,P,E', [
+    (dict(time_start=0, time_end=200), 1296, 80),     # 50 bins: five groups per SM, 810 items = more than one per group
+    (dict(time_start=0, time_end=200), 37, 3),        # one partial item
+    (dict(time_start=0, time_end=368), 1296, 70),     # 92 bins: four groups of 128 columns, six slots
+    (dict(time_start=0, time_end=320), 131, 40),      # 80 bins
+    (dict(time_start=0, time_end=16), 300, 33),       # 4 bins
+    (dict(time_start=-40, time_end=104), 70, 60),     # window that does not start at 0
+])
+def test_persistent_tensor_kernel_equals_the_cta_kernel(monkeypatch, window, P, E):
+    """k_generate_tensor_mega (one CTA per SM, 4-5 independent groups, each walking through its own
+    128-trace items) does the arithmetic of k_generate_tensor in the same order: identical cubes,
+    signal charges and analog sums, whatever the number of items per group."""
+    import torch
+    kw = dict(ACDC)
+    kw.update(window)
+    kw.update(n_pixels=P, nsb_rate=1.1, n_photon=12., time_signal=kw['time_start'] + 20)
+    out = {}
+    for mega in ('0', '1', '4'):
+        monkeypatch.setenv('DCT_TENSOR_MEGA', mega)
+        g = gen(seed=21, kernel='tensor', **kw)
+        adc, analog = g.generate_analog(E)
+        cube, t_sig, q_sig = g.generate(E, first_event=5, truth=True)
+        torch.cuda.synchronize()
+        out[mega] = (adc.clone(), analog.clone(), cube.clone(), t_sig.clone(), q_sig.clone())
+        g.close()
+    for mega in ('1', '4'):
+        for x, y in zip(out['0'], out[mega]):
+            assert torch.equal(x, y), mega
+    assert out['0'][0].float().std() > 1.0
+
+
 def test_auto_leaves_the_tensor_kernel_alone_when_its_rounding_would_show():
     """AUTO picks K1t only while the estimated fp16 rounding stays below 0.01 LSB: not for a gain of
     60 LSB per pe, nor for a window that starts after the pulse maximum (template scaled up ~30x)."""
