@@ -93,7 +93,7 @@ struct dct_handle {
     int16_t* d_chunk[2] = {nullptr, nullptr};
     float* d_sig[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int16_t* h_stage[2] = {nullptr, nullptr};
-    uint32_t chunk_events = 0;
+    uint32_t chunk_events = 0, chunk_unit = 0;      // largest chunk of the host pipeline, its unit [events]
     bool pipeline_ready = false;
 };
 
@@ -619,19 +619,17 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
     if (!h->pipeline_ready) {
         // chunk ~64 MiB: large enough to amortise launches, small enough to pipeline
         free_pipeline(h);                      // nothing half-built survives a failed earlier attempt
-        uint32_t ce = (uint32_t)std::max<size_t>(1, ((size_t)64 << 20) / trace_bytes);
+        // Chunks are multiples of a unit of ~16 MiB, at most four units (dct_generate_host ramps the
+        // sizes up and down again so that little of the first generation and of the last copy is exposed).
+        uint32_t unit = (uint32_t)std::max<size_t>(1, ((size_t)16 << 20) / trace_bytes);
         if (h->kernel == DCT_KERNEL_TENSOR && h->tc_mega_groups) {
             // The persistent kernel hands every group of every SM the same number of 128-trace items
-            // (+-1): take the chunk, up to 20 % smaller, that wastes the least of the last round.
+            // (+-1): a unit is what fills three rounds (517 instead of 438 C4 events per launch costs 9 %).
             const uint64_t slots = (uint64_t)h->sm_count * h->tc_mega_groups;
-            double best = -1.0;
-            const uint32_t n_hi = ce, n_lo = std::max<uint32_t>(1, ce - ce / 5);
-            for (uint32_t n = n_hi; n >= n_lo; --n) {
-                const uint64_t items = ((uint64_t)n * h->p.P + dct::TC_TRACES - 1) / dct::TC_TRACES;
-                const double eff = (double)items / (double)(((items + slots - 1) / slots) * slots);
-                if (eff > best + 1e-9) { best = eff; ce = n; }
-            }
+            unit = (uint32_t)std::max<uint64_t>(1, 3 * slots * dct::TC_TRACES / (uint64_t)h->p.P);
         }
+        h->chunk_unit = unit;
+        const uint32_t ce = 4 * unit;
         h->chunk_events = ce;
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
@@ -662,8 +660,22 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
             }
         }
 
-    const uint32_t ce = h->chunk_events;
-    const uint32_t n_chunks = (n_events + ce - 1) / ce;
+    // chunk sizes in units: 1, 2, 4, 4, ... 4, (rest), 2, 1
+    std::vector<uint32_t> chunk_end;
+    {
+        const uint32_t unit = h->chunk_unit;
+        const uint64_t U = ((uint64_t)n_events + unit - 1) / unit;
+        std::vector<uint32_t> sizes;
+        if (U <= 8) sizes.assign((size_t)U, 1);
+        else {
+            sizes = {1, 2};
+            for (uint64_t left = U - 6; left > 0; ) { const uint32_t k = (uint32_t)std::min<uint64_t>(4, left); sizes.push_back(k); left -= k; }
+            sizes.push_back(2); sizes.push_back(1);
+        }
+        uint64_t at = 0;
+        for (uint32_t k : sizes) { at = std::min<uint64_t>(n_events, at + (uint64_t)k * unit); chunk_end.push_back((uint32_t)at); }
+    }
+    const uint32_t n_chunks = (uint32_t)chunk_end.size();
     struct Pending { int16_t* dst; size_t bytes; bool live; } pend[2] = {{nullptr, 0, false}, {nullptr, 0, false}};
     // On any error: nothing may still be writing into the caller's buffer when we return.
     int rc = DCT_OK;
@@ -673,20 +685,34 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
     };
     for (uint32_t c = 0; c < n_chunks && rc == DCT_OK; ++c) {
         const int slot = (int)(c & 1);
-        const uint32_t e0 = c * ce, ne = std::min(ce, n_events - e0);
+        const uint32_t e0 = c ? chunk_end[c - 1] : 0, ne = chunk_end[c] - e0;
+        if (ne == 0) continue;
         // the slot's previous copy must have drained before we overwrite its device buffer
         if (c >= 2) {
-            if (!cuda_ok(cudaEventSynchronize(h->ev_copy[slot]), "cudaEventSynchronize")) break;
-            if (pend[slot].live) { memcpy(pend[slot].dst, h->h_stage[slot], pend[slot].bytes); pend[slot].live = false; }
+            if (pinned) {
+                // the generation stream waits by itself: every launch of the call is queued ahead of time
+                if (!cuda_ok(cudaStreamWaitEvent(h->s_gen, h->ev_copy[slot], 0), "cudaStreamWaitEvent")) break;
+            } else {
+                if (!cuda_ok(cudaEventSynchronize(h->ev_copy[slot]), "cudaEventSynchronize")) break;
+                if (pend[slot].live) { memcpy(pend[slot].dst, h->h_stage[slot], pend[slot].bytes); pend[slot].live = false; }
+            }
         }
-        rc = dct_generate(h, seed, first_event + e0, ne, h->d_chunk[slot],
-                          sig_time_host ? h->d_sig[slot][0] : nullptr,
-                          sig_charge_host ? h->d_sig[slot][1] : nullptr, h->s_gen);
+#ifdef DCT_HOST_DEBUG          // diagnosis builds: DCT_HOST_SKIP=gen / copy leaves one stage of the pipeline out
+        static const char* skip = getenv("DCT_HOST_SKIP");
+        const bool skip_gen = skip && !strcmp(skip, "gen"), skip_copy = skip && !strcmp(skip, "copy");
+#else
+        constexpr bool skip_gen = false, skip_copy = false;
+#endif
+        if (!skip_gen)
+            rc = dct_generate(h, seed, first_event + e0, ne, h->d_chunk[slot],
+                              sig_time_host ? h->d_sig[slot][0] : nullptr,
+                              sig_charge_host ? h->d_sig[slot][1] : nullptr, h->s_gen);
         if (rc) break;
         if (!cuda_ok(cudaEventRecord(h->ev_gen[slot], h->s_gen), "cudaEventRecord")) break;
         if (!cuda_ok(cudaStreamWaitEvent(h->s_copy, h->ev_gen[slot], 0), "cudaStreamWaitEvent")) break;
         int16_t* dst = adc_host + (size_t)e0 * h->p.P * h->p.B;
-        if (pinned) {
+        if (skip_copy) {
+        } else if (pinned) {
             if (!cuda_ok(cudaMemcpyAsync(dst, h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
         } else {
             if (!cuda_ok(cudaMemcpyAsync(h->h_stage[slot], h->d_chunk[slot], ne * trace_bytes, cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;

@@ -122,6 +122,22 @@ def test_host_path_equals_device_path():
     assert np.array_equal(buf, dev)
 
 
+@pytest.mark.parametrize('kernel,rate,n', [('sweep', 0.125, 1500), ('tensor', 1.0, 2300), ('tensor', 1.0, 200)])
+def test_host_path_with_the_ramped_chunk_schedule(kernel, rate, n):
+    """More than eight units of the host pipeline: chunks of 1, 2, 4 ... 4, 2, 1 units (for the persistent
+    tensor kernel a unit is three rounds of its groups), device-side slot hand-over for a pinned
+    destination, host-side for a pageable one -- the cube is the one of a single launch."""
+    g = gen(n_pixels=1296, nsb_rate=rate, n_photon=10., seed=5, kernel=kernel, **ACDC)
+    dev, t, q = cube(g, n, truth=True)
+    adc, th, qh = g.generate_host(n, first_event=0)
+    assert np.array_equal(adc.view(np.int16), dev)
+    assert np.array_equal(th, t) and np.array_equal(qh, q)
+    buf = np.empty((n, 1296, 50), dtype=np.int16)
+    g._handle.generate_host(g.seed, 0, n, buf.ctypes.data)
+    assert np.array_equal(buf, dev)
+    g.close()
+
+
 # ------------------------------------------------------------------ the samplers, one by one
 def _sample(kind, a=0.0, b=0.0, n=400000, seed=11):
     import torch
