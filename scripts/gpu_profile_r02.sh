@@ -7,5 +7,6 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_referen
 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 python bench.py --no-cpu-baseline > gpurun_out/plain_launch.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_bench_default.csv python bench.py --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 bash scripts/gpu_gen_prof.sh tensor c4 2048 tensor_final
+bash scripts/gpu_full_workloads.sh
 python scripts/sass_evidence.py gpurun_out/sass_evidence.txt
 cut -c1-600 gpurun_out/bench_n1.json; cut -c1-400 gpurun_out/bench_reference.json

@@ -37,6 +37,8 @@ with open(os.path.join(out_dir, 'SUMMARY.md'), 'w') as f:
             ('%.2f' % r['kernel_ms']) if r else '-', ('%.1f' % r['achieved']) if r else '-',
             ('%.4f' % r['frac']) if r else '-', ('%.3e' % e['value']) if e else '-',
             ('%.3e (%d)' % (c['value'], c['cores'])) if c else '-', k.get('sm_mhz', '-'), ','.join(k.get('reasons', [])) or 'none'))
+    f.write('\nRows with K1 = 38.2-38.3 ms (bench_c4_a, bench_scale_n*, bench_c5_full_1e7_n8) were taken with K1t as a CTA kernel, '
+            'the others with the persistent kernel that replaced it later in the round (36.8-37.1 ms).\n')
     f.write('\nncu summaries in this directory: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'ncu_*.txt')))) + '\n')
     f.write('\nLaunch lists: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'launches_*.csv')))) + '\n')
 import csv, collections
@@ -60,7 +62,7 @@ if os.path.exists(lp):
         if ev:
             f.write('In the CUDA-event timing of the same command K1 is %.1f of %.1f ms per step (%.0f %%).\n' % (
                 ev['roofline']['kernel_ms'], ev['ms_per_step'], 100 * ev['roofline']['kernel_ms'] / ev['ms_per_step']))
-        f.write('(Launches shorter than a full step are the 64 MiB chunks of the end-to-end leg and the iterator batches.)\n\n')
+        f.write('(Launches shorter than a full step are the chunks of the end-to-end leg and the iterator batches.)\n\n')
         f.write('| kernel | launches | total ms | share |\n|---|---|---|---|\n')
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| `%s` | %d | %.2f | %.1f %% |\n' % (k, v[0], v[1], 100 * v[1] / tot))
