@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <memory>
 
 #include "device_params.cuh"
 #include "generate.cuh"
@@ -62,6 +63,30 @@ struct DeviceArena {
 
 }  // namespace
 
+#include "host_transport.h"
+
+// 12-bit transport of dct_generate_host: SLOTS chunks in flight (generated, copied, being unpacked)
+#ifndef DCT_HOST_PACKED_DEFAULT
+#define DCT_HOST_PACKED_DEFAULT 0      // dct_generate_host: 12-bit transport when the ADC range allows it
+#endif
+struct PackedPipe {
+    static constexpr int SLOTS = 3;
+    unsigned char* d_buf[SLOTS] = {nullptr, nullptr, nullptr};
+    unsigned char* h_buf[SLOTS] = {nullptr, nullptr, nullptr};
+    float* d_sig[SLOTS][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t ev_gen[SLOTS] = {nullptr, nullptr, nullptr}, ev_copy[SLOTS] = {nullptr, nullptr, nullptr};
+    std::unique_ptr<dct::WorkerPool> pool;
+    ~PackedPipe() {
+        for (int i = 0; i < SLOTS; ++i) {
+            if (d_buf[i]) cudaFree(d_buf[i]);
+            if (h_buf[i]) cudaFreeHost(h_buf[i]);
+            for (int j = 0; j < 2; ++j) if (d_sig[i][j]) cudaFree(d_sig[i][j]);
+            if (ev_gen[i]) cudaEventDestroy(ev_gen[i]);
+            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+        }
+    }
+};
+
 struct dct_handle {
     int device = 0;
     int sm_count = 148;
@@ -95,6 +120,8 @@ struct dct_handle {
     int16_t* h_stage[2] = {nullptr, nullptr};
     uint32_t chunk_events = 0, chunk_unit = 0;      // largest chunk of the host pipeline, its unit [events]
     bool pipeline_ready = false;
+    int host_transport = 0;            // 0: int16 over PCIe, 1: 12-bit samples, widened by host threads
+    std::unique_ptr<PackedPipe> packed;
 };
 
 namespace {
@@ -170,6 +197,7 @@ void free_pipeline(dct_handle* h) {
     h->s_gen = h->s_copy = nullptr;
     h->chunk_events = 0;
     h->pipeline_ready = false;
+    h->packed.reset();
 }
 
 template <bool POLY, int NT>
@@ -539,7 +567,7 @@ static int stats_win_lo(const dct_handle* h, int win) { return (int)std::floor(h
 
 static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events, int16_t* adc,
                          float* sig_time, float* sig_charge, float* analog, void* stream,
-                         const dct::FusedStats* stats = nullptr) {
+                         const dct::FusedStats* stats = nullptr, bool pack12 = false) {
     if (!h || !adc) return fail(DCT_E_ARG, "handle or adc is NULL");
     if (n_events == 0) return DCT_OK;
     if ((first_event + n_events) >> 56) return fail(DCT_E_ARG, "event index exceeds 2^56");
@@ -555,6 +583,7 @@ static int generate_impl(dct_handle* h, uint64_t seed, uint64_t first_event, uin
     a.table_in_smem = h->table_in_smem ? 1 : 0;
     a.analog = analog;
     if (stats) a.st = *stats;
+    a.pack12 = pack12 ? 1 : 0;
     if (h->kernel == DCT_KERNEL_TENSOR) {
         dct::TensorArgs ta;
         ta.g = a;
@@ -609,6 +638,77 @@ int dct_generate_analog(dct_handle* h, uint64_t seed, uint64_t first_event, uint
     return generate_impl(h, seed, first_event, n_events, adc, nullptr, nullptr, analog, stream);
 }
 
+// chunk ends [events] of one dct_generate_host call; sizes in units: 1, 2, 4, 4, ... 4, (rest), 2, 1
+static std::vector<uint32_t> host_chunk_schedule(uint32_t unit, uint32_t n_events) {
+    const uint64_t U = ((uint64_t)n_events + unit - 1) / unit;
+    std::vector<uint32_t> sizes, chunk_end;
+    if (U <= 8) sizes.assign((size_t)U, 1);
+    else {
+        sizes = {1, 2};
+        for (uint64_t left = U - 6; left > 0; ) { const uint32_t k = (uint32_t)std::min<uint64_t>(4, left); sizes.push_back(k); left -= k; }
+        sizes.push_back(2); sizes.push_back(1);
+    }
+    uint64_t at = 0;
+    for (uint32_t k : sizes) {
+        const uint64_t next = std::min<uint64_t>(n_events, at + (uint64_t)k * unit);
+        if (next > at) chunk_end.push_back((uint32_t)next);
+        at = next;
+    }
+    return chunk_end;
+}
+
+// dct_generate_host with the 12-bit transport: the kernels write a chunk as a stream of 12-bit samples,
+// the copy engine brings it into a pinned staging slot, host threads widen it into the caller's buffer
+// (pinned or not).  Three slots: while one chunk is widened, the next two are generated and copied.
+static int generate_host_packed(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
+                                int16_t* adc_host, float* sig_time_host, float* sig_charge_host) {
+    PackedPipe& pp = *h->packed;
+    constexpr uint32_t K = PackedPipe::SLOTS;
+    const size_t trace_samples = (size_t)h->p.P * h->p.B;
+    const size_t sig_elems = (size_t)h->p.P * h->p.K;
+    const std::vector<uint32_t> chunk_end = host_chunk_schedule(h->chunk_unit, n_events);
+    const uint32_t n_chunks = (uint32_t)chunk_end.size();
+    int rc = DCT_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == DCT_OK) rc = fail(DCT_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    auto first_of = [&](uint32_t c) { return c ? chunk_end[c - 1] : 0u; };
+    uint32_t issued = 0, widened = 0;
+    while (widened < n_chunks && rc == DCT_OK) {
+        // keep the device busy: every free slot gets the next chunk (generation, then its copies)
+        while (issued < n_chunks && issued - widened < K && rc == DCT_OK) {
+            const uint32_t slot = issued % K, e0 = first_of(issued), ne = chunk_end[issued] - e0;
+            rc = generate_impl(h, seed, first_event + e0, ne, reinterpret_cast<int16_t*>(pp.d_buf[slot]),
+                               sig_time_host ? pp.d_sig[slot][0] : nullptr,
+                               sig_charge_host ? pp.d_sig[slot][1] : nullptr, nullptr, h->s_gen, nullptr, true);
+            if (rc) break;
+            const size_t bytes = (ne * trace_samples * 3 + 1) / 2;
+            if (!cuda_ok(cudaEventRecord(pp.ev_gen[slot], h->s_gen), "cudaEventRecord")) break;
+            if (!cuda_ok(cudaStreamWaitEvent(h->s_copy, pp.ev_gen[slot], 0), "cudaStreamWaitEvent")) break;
+            if (!cuda_ok(cudaMemcpyAsync(pp.h_buf[slot], pp.d_buf[slot], bytes, cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
+            if (sig_time_host &&
+                !cuda_ok(cudaMemcpyAsync(sig_time_host + (size_t)e0 * sig_elems, pp.d_sig[slot][0],
+                                         ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
+            if (sig_charge_host &&
+                !cuda_ok(cudaMemcpyAsync(sig_charge_host + (size_t)e0 * sig_elems, pp.d_sig[slot][1],
+                                         ne * sig_elems * sizeof(float), cudaMemcpyDeviceToHost, h->s_copy), "cudaMemcpyAsync")) break;
+            if (!cuda_ok(cudaEventRecord(pp.ev_copy[slot], h->s_copy), "cudaEventRecord")) break;
+            ++issued;
+        }
+        if (rc != DCT_OK || widened >= issued) break;
+        // the oldest chunk in flight: wait for its copy, widen it
+        const uint32_t slot = widened % K, e0 = first_of(widened), ne = chunk_end[widened] - e0;
+        if (!cuda_ok(cudaEventSynchronize(pp.ev_copy[slot]), "cudaEventSynchronize")) break;
+        dct::unpack12_parallel(*pp.pool, pp.h_buf[slot], adc_host + (size_t)e0 * trace_samples, ne * trace_samples);
+        ++widened;
+    }
+    // nothing may still be running on the handle's streams (or writing to the caller's truth arrays) on return
+    cuda_ok(cudaStreamSynchronize(h->s_copy), "cudaStreamSynchronize");
+    cuda_ok(cudaStreamSynchronize(h->s_gen), "cudaStreamSynchronize");
+    return rc;
+}
+
 int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_events,
                       int16_t* adc_host, float* sig_time_host, float* sig_charge_host) {
     if (!h || !adc_host) return fail(DCT_E_ARG, "handle or adc_host is NULL");
@@ -631,9 +731,34 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
         h->chunk_unit = unit;
         const uint32_t ce = 4 * unit;
         h->chunk_events = ce;
+        // transport: 12-bit samples when every ADC value fits (DCT_HOST_TRANSPORT=plain / packed12 overrides)
+        const char* tr = getenv("DCT_HOST_TRANSPORT");
+        const bool fits12 = h->p.adc_min >= 0 && h->p.adc_max <= 4095;
+        h->host_transport = (fits12 && (tr ? !strcmp(tr, "packed12") : DCT_HOST_PACKED_DEFAULT)) ? 1 : 0;
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        if (e == cudaSuccess && h->host_transport == 1) {
+            h->packed.reset(new (std::nothrow) PackedPipe());
+            if (!h->packed) { free_pipeline(h); return fail(DCT_E_NOMEM, "out of host memory"); }
+            PackedPipe& pp = *h->packed;
+            const size_t bytes = ((size_t)ce * h->p.P * h->p.B * 3 + 1) / 2 + 64;
+            for (int i = 0; i < PackedPipe::SLOTS && e == cudaSuccess; ++i) {
+                e = cudaEventCreateWithFlags(&pp.ev_gen[i], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pp.ev_copy[i], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaMalloc(&pp.d_buf[i], bytes);
+                if (e == cudaSuccess) e = cudaMallocHost(&pp.h_buf[i], bytes);
+                if (e == cudaSuccess) e = cudaMalloc(&pp.d_sig[i][0], ce * sig_elems * sizeof(float));
+                if (e == cudaSuccess) e = cudaMalloc(&pp.d_sig[i][1], ce * sig_elems * sizeof(float));
+            }
+            // host threads that widen the samples: a share of the cores, 2 .. 8 (DCT_HOST_THREADS overrides)
+            int n_gpu = 1;
+            cudaGetDeviceCount(&n_gpu);
+            int n_thr = (int)std::thread::hardware_concurrency() / (2 * std::max(1, n_gpu));
+            n_thr = std::min(8, std::max(2, n_thr));
+            if (const char* t = getenv("DCT_HOST_THREADS")) n_thr = std::min(64, std::max(1, atoi(t)));
+            pp.pool.reset(new dct::WorkerPool(n_thr));
+        }
+        for (int i = 0; i < 2 && e == cudaSuccess && h->host_transport == 0; ++i) {
             e = cudaEventCreateWithFlags(&h->ev_gen[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaMalloc(&h->d_chunk[i], ce * trace_bytes);
@@ -646,6 +771,8 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
         }
         h->pipeline_ready = true;
     }
+    if (h->host_transport == 1)
+        return generate_host_packed(h, seed, first_event, n_events, adc_host, sig_time_host, sig_charge_host);
     // Is the destination page-locked?  Then copy straight into it; otherwise go through pinned staging.
     cudaPointerAttributes attr;
     bool pinned = false;
@@ -660,21 +787,7 @@ int dct_generate_host(dct_handle* h, uint64_t seed, uint64_t first_event, uint32
             }
         }
 
-    // chunk sizes in units: 1, 2, 4, 4, ... 4, (rest), 2, 1
-    std::vector<uint32_t> chunk_end;
-    {
-        const uint32_t unit = h->chunk_unit;
-        const uint64_t U = ((uint64_t)n_events + unit - 1) / unit;
-        std::vector<uint32_t> sizes;
-        if (U <= 8) sizes.assign((size_t)U, 1);
-        else {
-            sizes = {1, 2};
-            for (uint64_t left = U - 6; left > 0; ) { const uint32_t k = (uint32_t)std::min<uint64_t>(4, left); sizes.push_back(k); left -= k; }
-            sizes.push_back(2); sizes.push_back(1);
-        }
-        uint64_t at = 0;
-        for (uint32_t k : sizes) { at = std::min<uint64_t>(n_events, at + (uint64_t)k * unit); chunk_end.push_back((uint32_t)at); }
-    }
+    const std::vector<uint32_t> chunk_end = host_chunk_schedule(h->chunk_unit, n_events);
     const uint32_t n_chunks = (uint32_t)chunk_end.size();
     struct Pending { int16_t* dst; size_t bytes; bool live; } pend[2] = {{nullptr, 0, false}, {nullptr, 0, false}};
     // On any error: nothing may still be writing into the caller's buffer when we return.
@@ -894,6 +1007,14 @@ int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     if (blocks > 0x7fffffffull) return fail(DCT_E_ARG, "too many traces for one launch");
     dct::k_dump_pe<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(d);
     CK(cudaGetLastError());
+    return DCT_OK;
+}
+
+int dct_test_unpack12(const unsigned char* packed, int16_t* out, uint64_t n_samples, uint32_t threads) {
+    if (!packed || !out) return fail(DCT_E_ARG, "packed or out is NULL");
+    if (threads == 0) { dct::unpack12_scalar(packed, out, (size_t)n_samples); return DCT_OK; }
+    dct::WorkerPool pool((int)std::min<uint32_t>(threads, 64));
+    dct::unpack12_parallel(pool, packed, out, (size_t)n_samples);
     return DCT_OK;
 }
 

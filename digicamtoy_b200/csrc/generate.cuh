@@ -71,6 +71,7 @@ struct GenArgs {
     int table_in_smem;          // generic coef32 table staged in shared memory
     float* analog = nullptr;    // test hook: [n_traces, B] analog sums (p.e.-weighted template) before digitisation
     FusedStats st;              // on-device statistics taken before the store (st.adc_hist == nullptr: off)
+    int pack12 = 0;             // host transport: `adc` is a byte stream of 12-bit samples (store_run_packed12)
 };
 
 // dynamic shared memory of a generation kernel: its own `base` bytes, then (statistics on) the
@@ -339,9 +340,62 @@ __device__ __forceinline__ void digitise_trace(const DevParams& p, const RoundKe
 
 // Coalesced store of the CTA's contiguous run of the cube: 16-byte streaming stores gathered from
 // the packed rows.  Output 32-bit word w of the run lives in row w / (B/2), word w % (B/2).
+// 12-bit transport of the host pipeline (dct_generate_host): the launch's samples as one little-endian
+// bit stream, sample s in bits [12 s, 12 s + 12) -- two samples per three bytes.  A CTA's run starts at
+// trace0 = k NT (NT a multiple of 32), i.e. at a multiple of 48 bytes: units of 32 samples = three
+// 16-byte stores; the last, partial unit goes out pair by pair.  Needs 0 <= ADC <= 4095 (the caller checks).
+template <int NT>
+__device__ __forceinline__ void store_run_packed12(const GenArgs& a, uint64_t trace0, const float* rows, const int tid) {
+    const int B = a.p.B, SB = row_stride(B);
+    const uint64_t left = a.n_traces - trace0;
+    const int n_live = (int)(left < (uint64_t)NT ? left : (uint64_t)NT);
+    const int n_s = n_live * B;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(a.adc) + (trace0 * (uint64_t)B / 2) * 3;
+    const uint16_t* halves = reinterpret_cast<const uint16_t*>(rows);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(rows);
+    const bool even = (B & 1) == 0;
+    const float inv_B = 1.0f / (float)B;
+    // samples s, s + 1 (s even) of the run as x0 | x1 << 12; a sample past the end reads as 0
+    auto pair = [&](int s) -> uint32_t {
+        int r = (int)(((float)s + 0.5f) * inv_B);            // exact: s < 2^16 (NT <= 256, B < 256)
+        int c = s - r * B;
+        if (even) {
+            const uint32_t w = words[r * SB + (c >> 1)];
+            return (w & 0xfffu) | ((w >> 4) & 0xfff000u);
+        }
+        const uint32_t x0 = halves[r * SB * 2 + c] & 0xfffu;
+        if (++c == B) { c = 0; ++r; }
+        const uint32_t x1 = (s + 1 < n_s) ? (halves[r * SB * 2 + c] & 0xfffu) : 0u;
+        return x0 | (x1 << 12);
+    };
+    const int n32 = n_s >> 5;
+    int4* dst4 = reinterpret_cast<int4*>(dst);
+    for (int u = tid; u < n32; u += NT) {
+        uint32_t w[12];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                         // 8 samples = four 24-bit pairs -> 3 words
+            const int s = 32 * u + 8 * q;
+            const uint32_t p0 = pair(s), p1 = pair(s + 2), p2 = pair(s + 4), p3 = pair(s + 6);
+            w[3 * q + 0] = p0 | (p1 << 24);
+            w[3 * q + 1] = (p1 >> 8) | (p2 << 16);
+            w[3 * q + 2] = (p2 >> 16) | (p3 << 8);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            __stcs(dst4 + 3 * u + q, make_int4((int)w[4 * q], (int)w[4 * q + 1], (int)w[4 * q + 2], (int)w[4 * q + 3]));
+    }
+    for (int s = 32 * n32 + 2 * tid; s < n_s; s += 2 * NT) {
+        const uint32_t p2 = pair(s);
+        unsigned char* d = dst + (s >> 1) * 3;
+        d[0] = (unsigned char)p2; d[1] = (unsigned char)(p2 >> 8);
+        if (s + 1 < n_s) d[2] = (unsigned char)(p2 >> 16);      // (a dangling last sample ends in the low nibble of d[1])
+    }
+}
+
 // (tid: index within the NT threads that store this run)
 template <int NT>
 __device__ __forceinline__ void store_run(const GenArgs& a, uint64_t trace0, const float* rows, const int tid) {
+    if (a.pack12) { store_run_packed12<NT>(a, trace0, rows, tid); return; }
     const int B = a.p.B, SB = row_stride(B);
     const uint64_t left = a.n_traces - trace0;
     const int n_live = (int)(left < (uint64_t)NT ? left : (uint64_t)NT);

@@ -17,7 +17,7 @@ LIB_NAME = 'libdigicamtoy_sm100.so'
 LIB_PATH = os.environ.get('DCT_LIB_PATH') or os.path.join(PACKAGE_DIR, LIB_NAME)    # (override: timing experiments against older builds)
 CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
 
-DCT_ABI_VERSION = 2
+DCT_ABI_VERSION = 3
 KERNEL_AUTO, KERNEL_SCATTER, KERNEL_SWEEP, KERNEL_GRID, KERNEL_TENSOR = 0, 1, 2, 3, 4
 KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 'sweep', KERNEL_GRID: 'grid',
                 KERNEL_TENSOR: 'tensor'}
@@ -25,7 +25,7 @@ KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 's
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',
     'dct_generate', 'dct_generate_stats', 'dct_generate_analog', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
-    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe',
+    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe', 'dct_test_unpack12',
 )
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -90,6 +90,8 @@ def load_library():
     lib.dct_write_calibrate.argtypes = [vp, ctypes.c_size_t, vp]
     lib.dct_trace_pe.argtypes = [vp, u64, u64, u32, u32, vp, vp, vp, vp, vp]
     lib.dct_test_sample.argtypes = [u32, ctypes.c_double, ctypes.c_double, u64, u32, vp, vp]
+    if hasattr(lib, 'dct_test_unpack12'):
+        lib.dct_test_unpack12.argtypes = [vp, vp, u64, u32]
     for name in EXPORTED_SYMBOLS:
         if name not in ('dct_last_error', 'dct_destroy') and hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
@@ -203,6 +205,15 @@ SAMPLERS = {'normal': 0, 'exp_gap': 1, 'borel': 2, 'poisson': 3, 'branching': 4,
 
 def test_sample(kind, a, b, seed, n, out_ptr, stream=None):
     check(load_library().dct_test_sample(SAMPLERS[kind], float(a), float(b), seed, n, out_ptr, stream))
+
+
+def test_unpack12(packed, n_samples, threads=0, offset=0):
+    """Host-only test hook: NumPy uint8 stream of 12-bit samples -> int16 array of n_samples
+    (``offset``: misalign the destination by that many int16)."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    out = np.empty(int(n_samples) + 32, dtype=np.int16)[int(offset):int(offset) + int(n_samples)]
+    check(load_library().dct_test_unpack12(packed.ctypes.data, out.ctypes.data, int(n_samples), int(threads)))
+    return out
 
 
 def export_config(params, path, adc_min=0, adc_max=4095, kernel=KERNEL_AUTO):

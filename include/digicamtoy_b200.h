@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DCT_ABI_VERSION 2
+#define DCT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DCT_API __attribute__((visibility("default")))
@@ -194,6 +194,11 @@ DCT_API int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uin
  * b primaries with Poisson(a) offspring, 5 uniform [0,1). */
 DCT_API int dct_test_sample(uint32_t kind, double a, double b, uint64_t seed, uint32_t n, float* out,
                             void* stream);
+
+/* Test hook, host only (no device needed): widens n_samples of the 12-bit transport stream of
+ * dct_generate_host (little-endian, sample s in bits [12 s, 12 s + 12)) into int16, on `threads`
+ * host threads (0: the scalar loop on the calling thread). */
+DCT_API int dct_test_unpack12(const unsigned char* packed, int16_t* out, uint64_t n_samples, uint32_t threads);
 
 #ifdef __cplusplus
 }

@@ -122,11 +122,13 @@ def test_host_path_equals_device_path():
     assert np.array_equal(buf, dev)
 
 
+@pytest.mark.parametrize('transport', ['plain', 'packed12'])
 @pytest.mark.parametrize('kernel,rate,n', [('sweep', 0.125, 1500), ('tensor', 1.0, 2300), ('tensor', 1.0, 200)])
-def test_host_path_with_the_ramped_chunk_schedule(kernel, rate, n):
+def test_host_path_with_the_ramped_chunk_schedule(monkeypatch, transport, kernel, rate, n):
     """More than eight units of the host pipeline: chunks of 1, 2, 4 ... 4, 2, 1 units (for the persistent
     tensor kernel a unit is three rounds of its groups), device-side slot hand-over for a pinned
     destination, host-side for a pageable one -- the cube is the one of a single launch."""
+    monkeypatch.setenv('DCT_HOST_TRANSPORT', transport)
     g = gen(n_pixels=1296, nsb_rate=rate, n_photon=10., seed=5, kernel=kernel, **ACDC)
     dev, t, q = cube(g, n, truth=True)
     adc, th, qh = g.generate_host(n, first_event=0)
@@ -135,6 +137,46 @@ def test_host_path_with_the_ramped_chunk_schedule(kernel, rate, n):
     buf = np.empty((n, 1296, 50), dtype=np.int16)
     g._handle.generate_host(g.seed, 0, n, buf.ctypes.data)
     assert np.array_equal(buf, dev)
+    g.close()
+
+
+@pytest.mark.parametrize('kw,n', [
+    (dict(n_pixels=7, time_start=0, time_end=204, kernel='scatter'), 333),      # odd P, odd B (51): byte-level tails
+    (dict(n_pixels=129, time_start=0, time_end=204, kernel='scatter'), 41),
+    (dict(n_pixels=33, time_start=0, time_end=200, kernel='sweep'), 1001),
+    (dict(n_pixels=300, time_start=0, time_end=200, sub_binning=1), 97),        # grid kernel
+    (dict(n_pixels=1, time_start=0, time_end=8, kernel='scatter'), 1),          # two samples in all
+    (dict(n_pixels=1, time_start=0, time_end=4, kernel='scatter'), 3),          # one sample per event, odd total
+])
+def test_packed_host_transport_equals_the_device_cube(monkeypatch, kw, n):
+    """dct_generate_host with DCT_HOST_TRANSPORT=packed12: the kernels write the chunk as a stream of
+    12-bit samples (store_run_packed12), host threads widen it -- same cube as dct_generate, for every
+    kernel, odd trace lengths and partial CTAs; pageable and pinned destinations; with saturating pulses."""
+    monkeypatch.setenv('DCT_HOST_TRANSPORT', 'packed12')
+    monkeypatch.setenv('DCT_HOST_THREADS', '3')
+    base = dict(ACDC)
+    base.update(kw)
+    g = gen(nsb_rate=0.6, n_photon=2000., seed=8, **base)
+    dev, t, q = cube(g, n, truth=True)
+    if base['time_end'] >= 200:
+        assert dev.max() == 4095                               # the rail is part of the test
+    adc, th, qh = g.generate_host(n, first_event=0)
+    assert np.array_equal(adc.view(np.int16), dev)
+    assert np.array_equal(th, t) and np.array_equal(qh, q)
+    buf = np.full(dev.shape, -1, dtype=np.int16)
+    g._handle.generate_host(g.seed, 0, n, buf.ctypes.data)
+    assert np.array_equal(buf, dev)
+    g.close()
+
+
+def test_packed_host_transport_is_not_used_when_the_adc_range_does_not_fit(monkeypatch):
+    """saturate=None lets the ADC leave [0, 4095]: the 12-bit transport must stand aside."""
+    monkeypatch.setenv('DCT_HOST_TRANSPORT', 'packed12')
+    g = gen(n_pixels=50, nsb_rate=0.6, n_photon=3000., seed=8, saturate=None, **{**ACDC, 'baseline': -50.})
+    dev = cube(g, 200)
+    assert dev.max() > 4095 and dev.min() < 0
+    adc = g.generate_host(200, first_event=0, truth=False)
+    assert np.array_equal(adc.view(np.int16), dev)
     g.close()
 
 

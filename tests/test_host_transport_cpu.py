@@ -1,0 +1,43 @@
+"""Host side of the 12-bit transport of dct_generate_host (csrc/host_transport.h): the widening of a
+packed stream into int16 -- scalar loop, AVX2 path and the thread pool -- against a NumPy packing of
+the same samples.  No GPU involved."""
+import numpy as np
+import pytest
+
+from digicamtoy_b200 import native
+
+
+def pack12(samples):
+    """NumPy reference of the stream the kernels write: sample s in bits [12 s, 12 s + 12), little endian."""
+    s = np.asarray(samples, dtype=np.uint32)
+    n = len(s)
+    if n % 2:
+        s = np.append(s, 0)
+    a, b = s[0::2], s[1::2]
+    out = np.empty((len(a), 3), dtype=np.uint8)
+    out[:, 0] = a & 0xff
+    out[:, 1] = (a >> 8) | ((b & 0xf) << 4)
+    out[:, 2] = b >> 4
+    out = out.reshape(-1)
+    return out[:(3 * n + 1) // 2]
+
+
+@pytest.mark.parametrize('n', [0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 48, 49, 1000, 64801, (1 << 20) + 5, 3 * (1 << 20) + 1])
+@pytest.mark.parametrize('threads,offset', [(0, 0), (1, 0), (3, 0), (1, 2), (1, 1), (2, 7)])
+def test_unpack12_equals_the_numpy_packing(n, threads, offset):
+    rs = np.random.RandomState(n % 9973 + threads)
+    x = rs.randint(0, 4096, size=n).astype(np.int16)
+    if n > 4:
+        x[:4] = [0, 4095, 1, 4094]
+    packed = pack12(x)
+    assert len(packed) == (3 * n + 1) // 2
+    # guard bytes behind the stream: the widening must not depend on what follows it
+    padded = np.concatenate([packed, rs.randint(0, 256, size=64).astype(np.uint8)])
+    out = native.test_unpack12(padded, n, threads, offset)      # offsets: streaming stores after a peel / unaligned stores
+    assert out.dtype == np.int16 and np.array_equal(out, x)
+
+
+def test_unpack12_rejects_null_pointers():
+    lib = native.load_library()
+    assert lib.dct_test_unpack12(None, None, 4, 0) != 0
+    assert b'NULL' in lib.dct_last_error()
