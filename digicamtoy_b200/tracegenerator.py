@@ -145,8 +145,16 @@ class NTraceGenerator:
                                      adc_max=self.saturate[1], kernel=_KERNELS[kernel])
         self.kernel = self._handle.kernel
         if batch_events is None:
-            # ~32 MiB of ADC per batch keeps the per-event iterator responsive
-            batch_events = max(1, min(4096, (32 << 20) // (p.n_pixels * p.n_bins * 2)))
+            # Iterator batches: ~128 MiB of ADC for long runs -- generation and copy overlap inside a
+            # batch, 3.5e5 instead of 2.1e5 C4 events/s (scripts/iterator_batch.py) -- but ~32 MiB for
+            # runs below 20000 events: pinning memory costs ~0.3 ms per MiB, as much as simulating
+            # 10^4 events.
+            long_run = n_events is None or int(n_events) >= 20000
+            batch_events = max(1, min(4096, ((128 if long_run else 32) << 20) // (p.n_pixels * p.n_bins * 2)))
+            # the first batches of a long run are small (the first event arrives after ~32 MiB, not 128)
+            self._first_batch = max(1, min(batch_events, (32 << 20) // (p.n_pixels * p.n_bins * 2)))
+        else:
+            self._first_batch = int(batch_events)
         self.batch_events = int(batch_events)
         self._host = None          # (adc, time, charge) views of the current batch
         self._bufs = [None, None]  # the two pinned batch slots of the iterator
@@ -321,11 +329,13 @@ class NTraceGenerator:
         return (a, t.numpy(), q.numpy()) if truth else a
 
     # ------------------------------------------------------------------ internals
-    def _batch_buffers(self, which):
-        """Pinned (adc, time, charge) tensors of iterator batch slot `which` (0 / 1), allocated once."""
+    def _batch_buffers(self, which, n_needed):
+        """Pinned (adc, time, charge) tensors of iterator batch slot `which` (0 / 1) for n_needed events."""
         torch = _torch()
-        if self._bufs[which] is None:
-            p, n = self.params, self.batch_events
+        if self._bufs[which] is None or self._bufs[which][0].shape[0] < n_needed:
+            p, n = self.params, int(n_needed)
+            if self._bufs[which] is not None:                    # growing: straight to the full batch size, once per slot
+                n = max(n, self.batch_events if self.n_events is None else min(self.batch_events, int(self.n_events)))
             self._bufs[which] = (torch.empty((n, p.n_pixels, p.n_bins), dtype=torch.int16).pin_memory(),
                                  torch.empty((n, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory(),
                                  torch.empty((n, p.n_pixels, p.n_pulses), dtype=torch.float32).pin_memory())
@@ -333,7 +343,7 @@ class NTraceGenerator:
 
     def _generate_batch(self, which, first_relative, n):
         """Batch [first_relative, +n) into slot `which`; returns NumPy views like generate_host."""
-        adc, t, q = self._batch_buffers(which)
+        adc, t, q = self._batch_buffers(which, n)
         self._handle.generate_host(self.seed, self.first_event + first_relative, n, adc.data_ptr(),
                                    t.data_ptr(), q.data_ptr())
         a = adc.numpy()[:n]
@@ -342,7 +352,7 @@ class NTraceGenerator:
         return a, t.numpy()[:n], q.numpy()[:n]
 
     def _batch_size_at(self, first_relative):
-        n = self.batch_events
+        n = min(self.batch_events, max(self._first_batch, int(first_relative)))     # 1, 1, 2, 4 ... first batches
         if self.n_events is not None:
             n = max(0, min(n, self.n_events - first_relative))
         return n

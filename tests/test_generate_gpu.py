@@ -879,6 +879,30 @@ def test_iterator_prefetches_into_two_reused_pinned_batches():
     g.close(); g1.close(); g2.close()
 
 
+def test_iterator_batches_of_a_long_run_grow_from_32_to_128_mib():
+    """Open-ended (or >= 20000-event) runs: batches of 258, 258, 516, 1032, 1035 ... C4 events -- the first
+    event arrives after a 32 MiB batch, the steady state runs on 128 MiB batches (generation and copy
+    overlap inside a batch); each slot is re-pinned once, at the full size.  Same events as the bulk call."""
+    import torch
+    kw = dict(n_pixels=1296, nsb_rate=0.04, n_photon=2., seed=23, **ACDC)
+    g = gen(**kw)
+    assert (g._first_batch, g.batch_events) == (258, 1035)
+    assert gen(n_events=5000, **kw).batch_events == 258                     # short run: small batches only
+    bulk = gen(**kw).generate(2400)
+    torch.cuda.synchronize()
+    starts = []
+    for ev in g:
+        if ev.count == g._batch_first:
+            starts.append(ev.count)
+        if ev.count % 7 == 0 or ev.count == g._batch_first or ev.count == g._batch_first + g._batch_len - 1:
+            assert np.array_equal(np.asarray(ev.adc_count).astype(np.int16), bulk[ev.count].cpu().numpy()), ev.count
+        if ev.count == 2399:
+            break
+    assert starts == [0, 258, 516, 1032, 2064]
+    assert g._bufs[0][0].shape[0] == 1035 and g._bufs[1][0].shape[0] == 1035
+    g.close()
+
+
 def test_pe_list_attributes_of_the_iterator():
     toy = gen(n_pixels=20, nsb_rate=0.3, n_photon=3., n_events=3, seed=8, **ACDC)
     assert toy.nsb_time.shape == (20, 1) and not toy.mask.any()          # before the first event (:194-196)
