@@ -37,7 +37,7 @@ with open(os.path.join(out_dir, 'SUMMARY.md'), 'w') as f:
             ('%.2f' % r['kernel_ms']) if r else '-', ('%.1f' % r['achieved']) if r else '-',
             ('%.4f' % r['frac']) if r else '-', ('%.3e' % e['value']) if e else '-',
             ('%.3e (%d)' % (c['value'], c['cores'])) if c else '-', k.get('sm_mhz', '-'), ','.join(k.get('reasons', [])) or 'none'))
-    f.write('\nRows with K1 = 38.2-38.3 ms (bench_c4_a, bench_scale_n*, bench_c5_full_1e7_n8) were taken with K1t as a CTA kernel, '
+    f.write('\nRows with K1 = 38.2-38.3 ms (bench_c4_a, bench_c5_full_1e7_n8) were taken with K1t as a CTA kernel, '
             'the others with the persistent kernel that replaced it later in the round (36.8-37.1 ms).\n')
     f.write('\nncu summaries in this directory: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'ncu_*.txt')))) + '\n')
     f.write('\nLaunch lists: ' + ', '.join(sorted(os.path.basename(p) for p in glob.glob(os.path.join(out_dir, 'launches_*.csv')))) + '\n')
