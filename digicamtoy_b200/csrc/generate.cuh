@@ -291,7 +291,29 @@ __device__ __forceinline__ void add_signal_pulses(const GenArgs& a, const TraceI
             float y0 = __fmaf_rn((float)b1, p.dt, -s);
             if (y0 < 0.0f) { y0 += p.dt; ++b1; }
             if (y0 >= p.dt) { y0 -= p.dt; --b1; }
-            scatter_generic(p, coef, row, b1, y0, A);
+            if (p.n_phase > 0) {
+                // sampling period = whole number of knot steps: every tap of the pulse sits in the same
+                // phase, at the same offset u of its knot interval (tap j <-> interval f + n_phase j):
+                // one (f, u), then a load and four FMA per bin -- a third of scatter_generic's
+                // instructions (10 % of the dark.yml kernel, profiles/r02/ncu_dark_sweep_r02.txt)
+                int f; float u;
+                phase_of(p, y0, f, u);
+                const int kb = b1 - p.n_drop;
+                const int j_hi = min(p.n_taps, p.B - kb);
+                const float4* tab = p.poly + f;
+                for (int j = max(0, -kb); j < j_hi; ++j)
+                    row[kb + j] = __fmaf_rn(A, horner(__ldg(tab + j * p.n_phase), u), row[kb + j]);
+                // The template's right end is inclusive (interp1d, reference :141-143): a bin exactly at
+                // y = L belongs to the last knot interval, one past where the phase table puts it.  Not
+                // a measure-zero case here: time_signal on a sample with jitter = 0 is the usual config.
+                for (int j = p.n_taps - 1; j <= p.n_taps; ++j) {
+                    const float y = __fmaf_rn((float)j, p.dt, y0);
+                    if (y == p.L && f + p.n_phase * j >= p.n_iv && (unsigned)(kb + j) < (unsigned)p.B)
+                        row[kb + j] = __fmaf_rn(A, template_at(p, coef, y), row[kb + j]);
+                }
+            } else {
+                scatter_generic(p, coef, row, b1, y0, A);
+            }
         }
     }
 }
