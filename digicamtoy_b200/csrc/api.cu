@@ -66,6 +66,10 @@ struct DeviceArena {
 #include "host_transport.h"
 
 // 12-bit transport of dct_generate_host: SLOTS chunks in flight (generated, copied, being unpacked)
+#ifndef DCT_STATS_WIDE_SHIFT
+#define DCT_STATS_WIDE_SHIFT 5.0       // NSB pedestal shift [LSB] from which K3 skips its thread-private histogram columns
+                                       // (measured, profiles/r02/stats_wide.txt: K3 1.92 -> 1.64 ms on C4, 1.49 -> 1.27 ms at 0.125 GHz)
+#endif
 #ifndef DCT_HOST_PACKED_DEFAULT
 #define DCT_HOST_PACKED_DEFAULT 0      // dct_generate_host: 12-bit transport when the ADC range allows it
 #endif
@@ -926,7 +930,12 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
     if (fast) {
         // histogram windows: centred on the expected pedestal (true_baseline, host-computed) and on
         // the charge of a trace that holds nothing but that pedestal shift
-        const int win_lo = stats_win_lo(h, dct::STATS_WIN);
+        int win_lo = stats_win_lo(h, dct::STATS_WIN);
+        // Cubes with a night-sky pedestal spread far beyond the 16 thread-private values (C4: sigma ~ 30 LSB)
+        // would split every warp between the private columns and the CTA histogram, sample by sample:
+        // there every sample goes to the CTA histogram (a window no value can reach), one path for the warp.
+        const int ped_lo = win_lo;                     // where the pedestal is: the compact CTA histogram is placed around it
+        if ((h->mean_true_baseline - h->mean_baseline) > DCT_STATS_WIDE_SHIFT) win_lo = 0x3fffffff;
         // Quiet cubes (no pulse taller than ~100 LSB and an NSB pedestal shift below 3 LSB: dark runs) keep everything within
         // a few hundred values of the pedestal: a 512-value histogram slice and a 256-bin charge window
         // leave room for one more CTA per SM (measured on dark.yml: 2.45 -> 2.20 ms per 16384 events; the
@@ -945,7 +954,7 @@ int dct_stats_accumulate(dct_handle* h, const int16_t* adc, uint32_t n_events,
         const int n_hist_s = compact ? compact_hist : n_hist;
         int hist_lo = a.adc_min;
         if (compact) {
-            hist_lo = win_lo - compact_hist / 8;
+            hist_lo = ped_lo - compact_hist / 8;
             hist_lo = std::max(a.adc_min, std::min(hist_lo, a.adc_max + 1 - n_hist_s));
         }
         const size_t tile_words = ((size_t)dct::STATS_ROWS * wpr + 3) & ~(size_t)3;

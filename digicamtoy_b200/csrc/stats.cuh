@@ -118,6 +118,8 @@ k_stats(const StatsArgs a) {
 //     each event's 128 rows are one contiguous run of the cube, brought into shared memory with
 //     16-byte cp.async (one buffer in the compact layout, else two) and then read row-wise.
 //   * per sample: a plain 16-bit read-modify-write of the thread-private histogram column (window of
+//     [wide cubes -- NSB pedestal spread far beyond the window -- get win_lo out of reach from the host:
+//      every sample then takes the CTA-histogram path and the warp does not split, ncu_k3_c4_r02.txt]
 //     STATS_WIN (16) values around the pedestal; the rare sample outside goes to the CTA histogram with
 //     an atomic), and integer sums for the per-trace / per-pixel quantities.
 //   * per bin: a second pass over the tile with lane = word column, accumulated in 64-bit registers.
