@@ -1019,6 +1019,13 @@ int dct_trace_pe(dct_handle* h, uint64_t seed, uint64_t first_event, uint32_t n_
     return DCT_OK;
 }
 
+int dct_test_chunk_schedule(uint32_t unit, uint32_t n_events, uint32_t* ends, uint32_t cap) {
+    if (!ends || unit == 0) { fail(DCT_E_ARG, "ends is NULL or unit is 0"); return -1; }
+    const std::vector<uint32_t> e = host_chunk_schedule(unit, n_events);
+    for (size_t i = 0; i < e.size() && i < cap; ++i) ends[i] = e[i];
+    return (int)e.size();
+}
+
 int dct_test_unpack12(const unsigned char* packed, int16_t* out, uint64_t n_samples, uint32_t threads) {
     if (!packed || !out) return fail(DCT_E_ARG, "packed or out is NULL");
     if (threads == 0) { dct::unpack12_scalar(packed, out, (size_t)n_samples); return DCT_OK; }

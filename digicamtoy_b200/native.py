@@ -25,7 +25,7 @@ KERNEL_NAMES = {KERNEL_AUTO: 'auto', KERNEL_SCATTER: 'scatter', KERNEL_SWEEP: 's
 EXPORTED_SYMBOLS = (
     'dct_abi_version', 'dct_last_error', 'dct_create', 'dct_destroy', 'dct_selected_kernel',
     'dct_generate', 'dct_generate_stats', 'dct_generate_analog', 'dct_generate_host', 'dct_replay_f64', 'dct_replay_f32',
-    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe', 'dct_test_unpack12',
+    'dct_stats_accumulate', 'dct_write_calibrate', 'dct_test_sample', 'dct_trace_pe', 'dct_test_unpack12', 'dct_test_chunk_schedule',
 )
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -92,6 +92,8 @@ def load_library():
     lib.dct_test_sample.argtypes = [u32, ctypes.c_double, ctypes.c_double, u64, u32, vp, vp]
     if hasattr(lib, 'dct_test_unpack12'):
         lib.dct_test_unpack12.argtypes = [vp, vp, u64, u32]
+    if hasattr(lib, 'dct_test_chunk_schedule'):
+        lib.dct_test_chunk_schedule.argtypes = [u32, u32, vp, u32]
     for name in EXPORTED_SYMBOLS:
         if name not in ('dct_last_error', 'dct_destroy') and hasattr(lib, name):
             getattr(lib, name).restype = ctypes.c_int
@@ -214,6 +216,15 @@ def test_unpack12(packed, n_samples, threads=0, offset=0):
     out = np.empty(int(n_samples) + 32, dtype=np.int16)[int(offset):int(offset) + int(n_samples)]
     check(load_library().dct_test_unpack12(packed.ctypes.data, out.ctypes.data, int(n_samples), int(threads)))
     return out
+
+
+def test_chunk_schedule(unit, n_events):
+    """Host-only test hook: chunk ends [events] of a dct_generate_host call."""
+    ends = np.zeros(1 << 16, dtype=np.uint32)
+    n = load_library().dct_test_chunk_schedule(int(unit), int(n_events), ends.ctypes.data, len(ends))
+    if n < 0:
+        raise RuntimeError(load_library().dct_last_error().decode())
+    return ends[:n].copy()
 
 
 def export_config(params, path, adc_min=0, adc_max=4095, kernel=KERNEL_AUTO):

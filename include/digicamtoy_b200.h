@@ -200,6 +200,11 @@ DCT_API int dct_test_sample(uint32_t kind, double a, double b, uint64_t seed, ui
  * host threads (0: the scalar loop on the calling thread). */
 DCT_API int dct_test_unpack12(const unsigned char* packed, int16_t* out, uint64_t n_samples, uint32_t threads);
 
+/* Test hook, host only: the chunk ends [events] dct_generate_host would use for a call of n_events with a
+ * chunk unit of `unit` events (sizes 1, 2, 4 ... 4, rest, 2, 1 units).  Writes at most `cap` ends to
+ * `ends` and returns the number of chunks (negative on error). */
+DCT_API int dct_test_chunk_schedule(uint32_t unit, uint32_t n_events, uint32_t* ends, uint32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

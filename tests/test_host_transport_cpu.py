@@ -41,3 +41,24 @@ def test_unpack12_rejects_null_pointers():
     lib = native.load_library()
     assert lib.dct_test_unpack12(None, None, 4, 0) != 0
     assert b'NULL' in lib.dct_last_error()
+
+
+@pytest.mark.parametrize('unit,n', [(219, 16384), (219, 1), (219, 219), (219, 220), (219, 8 * 219), (219, 8 * 219 + 1),
+                                    (129, 1500), (1, 7), (1, 100), (10168, 53), (73, 10 ** 6)])
+def test_chunk_schedule_of_the_host_pipeline(unit, n):
+    """dct_generate_host walks a request in chunks of 1, 2, 4 ... 4, rest, 2, 1 units (all of one unit up to
+    eight units): contiguous, no empty chunk, nothing larger than the four-unit device buffers."""
+    ends = native.test_chunk_schedule(unit, n).astype(np.int64)
+    sizes = np.diff(np.concatenate([[0], ends]))
+    assert ends[-1] == n and (sizes > 0).all() and sizes.max() <= 4 * unit
+    units = -(-n // unit)
+    if units <= 8:
+        assert len(sizes) == units and (sizes[:-1] == unit).all()
+    else:
+        assert list(sizes[:2]) == [unit, 2 * unit] and sizes[-1] <= unit and sizes[-2] <= 2 * unit
+        assert (sizes[2:-3] == 4 * unit).all()                      # the middle: full buffers, then one rest
+
+
+def test_chunk_schedule_rejects_bad_arguments():
+    lib = native.load_library()
+    assert lib.dct_test_chunk_schedule(0, 10, None, 0) < 0
