@@ -587,6 +587,9 @@ def _check_stats_against_numpy(g, out, charge_lo, n_charge_bins, pieces=(None,))
     ('tile-compact-bright', dict(n_pixels=130, n_photon=[[3000.]] * 65 + [[40.]] * 65,            # saturating half
                                  **{**DARK, 'time_signal': 100.}), 200),
     ('tile-compact-128', dict(n_pixels=33, nsb_rate=0.2, n_photon=300., **{**ACDC, 'time_end': 512}), 120),
+    ('tile-70-bins', dict(n_pixels=150, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 280}), 90),    # 35 words: half-warps share 3 columns
+    ('tile-96-bins', dict(n_pixels=77, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 384}), 90),     # 48 words: ... 16 columns
+    ('tile-98-bins', dict(n_pixels=77, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 392}), 90),     # 49 words: one lane per column again
     ('generic-long', dict(n_pixels=20, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 800}), 60),
     ('generic-odd', dict(n_pixels=20, nsb_rate=0.2, n_photon=30., **{**ACDC, 'time_end': 204}), 60),
 ])
