@@ -87,6 +87,24 @@ __device__ __forceinline__ void slide_window(float (&W)[TAPS], bool go) {
         : "r"((int)go));
 }
 
+// W[j] <- W[j+S] (j < TAPS-S), the last S <- 0, for the lanes with `go`: one predicated move per
+// register, in place like slide_window (used for gaps of several cells: 2, 4, 8 and 16 at a time).
+template <int S>
+__device__ __forceinline__ void slide_by(float (&W)[22], bool go) {
+    static_assert(S >= 1 && S < 22, "window of 22 taps");
+    const int g = (int)go;
+#pragma unroll
+    for (int j = 0; j + S < 22; ++j)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mov.f32 %0, %1;\n\t}" : "+f"(W[j]) : "f"(W[j + S]), "r"(g));
+#pragma unroll
+    for (int j = 22 - S; j < 22; ++j)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p mov.f32 %0, 0f00000000;\n\t}" : "+f"(W[j]) : "r"(g));
+}
+
+#ifndef DCT_SWEEP_BINARY_SLIDE
+#define DCT_SWEEP_BINARY_SLIDE 1      // gaps of 2 .. 22 cells: slide by 2, 4, 8, 16 (binary digits of the gap) instead of cell by cell
+#endif
+
 template <int TAPS, int PHASES, int NT>
 __global__ void __launch_bounds__(NT, DCT_SWEEP_MIN_BLOCKS)
 k_generate_sweep(const GenArgs a) {
@@ -138,7 +156,7 @@ k_generate_sweep(const GenArgs a) {
 #if !DCT_EXP_NO_SLIDE
                 slide_window<TAPS>(W, one);
 #endif
-                if (k >= 2) {                                 // rare: gap longer than a cell
+                if (k >= 2) {                                 // gap longer than a cell (rare at 1 GHz, the rule below 0.2 GHz)
                     ++kb;
                     if (k > TAPS) {
 #pragma unroll
@@ -147,12 +165,33 @@ k_generate_sweep(const GenArgs a) {
                             W[j] = 0.0f;
                         }
                     } else {
+#if DCT_SWEEP_BINARY_SLIDE
+                        // k - 1 more cells, 1 .. 21 = binary digits: retire the S oldest bins, slide by S.
+                        // At most five short steps per warp, where the cell-by-cell loop ran to the
+                        // longest gap of the warp with two lanes active (profiles/r02/ncu_acdc_sweep_r02.txt).
+                        const int m = k - 1;
+#define DCT_SLIDE_STEP(S)                                                                   \
+                        if (m & S) {                                                        \
+                            _Pragma("unroll")                                               \
+                            for (int j = 0; j < S; ++j)                                     \
+                                if ((unsigned)(kb + j) < (unsigned)B) row[kb + j] = W[j];   \
+                            slide_by<S>(W, true);                                           \
+                            kb += S;                                                        \
+                        }
+                        DCT_SLIDE_STEP(1)
+                        DCT_SLIDE_STEP(2)
+                        DCT_SLIDE_STEP(4)
+                        DCT_SLIDE_STEP(8)
+                        DCT_SLIDE_STEP(16)
+#undef DCT_SLIDE_STEP
+#else
                         for (--k; k > 0; --k, ++kb) {
                             if ((unsigned)kb < (unsigned)B) row[kb] = W[0];
 #pragma unroll
                             for (int j = 0; j < TAPS - 1; ++j) W[j] = W[j + 1];
                             W[TAPS - 1] = 0.0f;
                         }
+#endif
                     }
                 }
                 int f; float u;

@@ -94,11 +94,12 @@ inline TensorLayout tensor_layout(int B, int n_drop, int cell0, int n_cells, int
 #ifndef DCT_TC_REFRESH_LIMIT
 #define DCT_TC_REFRESH_LIMIT 0                 // 1: look at the released-cell counter before every store, not once per group
 #endif
-// mean pe per trace from which AUTO prefers this kernel over the sweep kernel: measured crossover
-// at 55-60 pe / trace (0.25 GHz on the 240 ns window: 11.3 against 11.6 ms per 8192 events; profiles/r02/crossover_tensor.txt) -- below it the
-// per-cell hand-over (59 cells whatever the rate) costs more than the taps it saves.
+// mean pe per trace from which AUTO prefers this kernel over the sweep kernel: measured crossover at
+// ~65 pe / trace (0.25 GHz on the 240 ns window = 60 pe: sweep 10.5 against 10.9 ms per 8192 events,
+// 0.4 GHz = 96 pe: 14.6 against 12.1; profiles/r02/crossover_tensor.txt) -- below it the per-cell
+// hand-over (59 cells whatever the rate) costs more than the taps it saves.
 #ifndef DCT_TC_MIN_MEAN_PE
-#define DCT_TC_MIN_MEAN_PE 60.0
+#define DCT_TC_MIN_MEAN_PE 66.0
 #endif
 
 struct TensorArgs {
