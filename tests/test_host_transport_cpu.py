@@ -62,3 +62,21 @@ def test_chunk_schedule_of_the_host_pipeline(unit, n):
 def test_chunk_schedule_rejects_bad_arguments():
     lib = native.load_library()
     assert lib.dct_test_chunk_schedule(0, 10, None, 0) < 0
+
+
+def test_iterator_batch_sizes_ramp_up_on_long_runs():
+    """NTraceGenerator._batch_size_at (host logic, no device): the first batches of a long run are small
+    (32 MiB), then double up to the 128 MiB steady state; a run with a known end never asks for more
+    than it has left."""
+    from digicamtoy_b200.tracegenerator import NTraceGenerator
+    g = object.__new__(NTraceGenerator)
+    g.batch_events, g._first_batch, g.n_events = 1035, 258, None
+    starts, at = [], 0
+    for _ in range(7):
+        starts.append((at, g._batch_size_at(at)))
+        at += starts[-1][1]
+    assert starts == [(0, 258), (258, 258), (516, 516), (1032, 1032), (2064, 1035), (3099, 1035), (4134, 1035)]
+    g.n_events = 3000
+    assert g._batch_size_at(2064) == 936 and g._batch_size_at(3000) == 0
+    g.batch_events, g._first_batch, g.n_events = 10, 10, 53          # explicit batch size: no ramp
+    assert [g._batch_size_at(k) for k in (0, 10, 50)] == [10, 10, 3]
